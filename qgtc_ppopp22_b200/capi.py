@@ -1,0 +1,192 @@
+"""ctypes mirror of the C ABI (include/qgtc_b200.h) on torch CUDA tensors.
+
+Function names, argument order and returned shapes follow the reference's Python surface
+(QGTC_module/QGTC_host.cpp:106-256); every call goes through ``libqgtc_b200.so`` -- the same entry
+points a cgo/JNI/ctypes binding of another host would use.  No CPU fallback exists: loading fails
+loudly when the library is not built.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import lib_dir
+
+ENGINE_AUTO, ENGINE_MMA_SYNC, ENGINE_TCGEN05 = 0, 1, 2
+FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK = 0x1, 0x2
+LAYOUT_ROW, LAYOUT_COL128, LAYOUT_COL8 = 0, 1, 2
+
+# every symbol include/qgtc_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "qgtc_abi_version", "qgtc_strerror", "qgtc_last_cuda_error", "qgtc_packed_words", "qgtc_packed_shape",
+    "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
+    "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
+]
+
+_LIB = None
+
+
+class QgtcError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(lib_dir(), "libqgtc_b200.so")
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("libqgtc_b200.so is not built (%s); run __graft_entry__.build(). No CPU fallback." % path)
+        L = ctypes.CDLL(path)
+        c = ctypes
+        vp, sz, i = c.c_void_p, c.c_size_t, c.c_int
+        L.qgtc_abi_version.restype = i
+        L.qgtc_strerror.restype = c.c_char_p
+        L.qgtc_strerror.argtypes = [i]
+        L.qgtc_last_cuda_error.restype = c.c_char_p
+        L.qgtc_packed_words.restype = sz
+        L.qgtc_packed_words.argtypes = [i, i, i, i]
+        L.qgtc_packed_shape.restype = None
+        L.qgtc_packed_shape.argtypes = [i, i, i, i, c.POINTER(c.c_int64), c.POINTER(c.c_int64)]
+        L.qgtc_val2bit.argtypes = [vp, i, i, i, i, i, vp, sz, vp]
+        L.qgtc_bit2val.argtypes = [vp, sz, i, i, i, i, i, vp, vp]
+        L.qgtc_bitmm2bit.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm2bit_col.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm2int.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_tile_counts.argtypes = [vp, sz, i, i, i, i, i, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), vp]
+        L.qgtc_bitmm2bit_batched.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm2bit_host.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_launch_count.restype = c.c_uint64
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int, op: str) -> None:
+    if rc != 0:
+        L = lib()
+        msg = L.qgtc_strerror(rc).decode()
+        if rc == 5:
+            msg += ": " + L.qgtc_last_cuda_error().decode()
+        raise QgtcError("%s: %s" % (op, msg))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def packed_shape(layout: int, bits: int, H: int, W: int) -> tuple[int, int]:
+    r, c = ctypes.c_int64(0), ctypes.c_int64(0)
+    lib().qgtc_packed_shape(layout, bits, H, W, ctypes.byref(r), ctypes.byref(c))
+    return int(r.value), int(c.value)
+
+
+def packed_words(layout: int, bits: int, H: int, W: int) -> int:
+    return int(lib().qgtc_packed_words(layout, bits, H, W))
+
+
+def launch_count() -> int:
+    return int(lib().qgtc_launch_count())
+
+
+def _req_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise QgtcError("%s must be a CUDA tensor" % name)
+    if not t.is_contiguous():
+        raise QgtcError("%s must be contiguous" % name)
+    if t.dtype != dtype:
+        raise QgtcError("%s must be %s" % (name, dtype))
+    return t
+
+
+def val2bit(x: torch.Tensor, nbits: int, col_major: bool, output_layer: bool) -> torch.Tensor:
+    """QGTC.val2bit (QGTC_host.cpp:229-238)."""
+    _req_cuda(x, torch.float32, "input")
+    H, W = x.shape
+    layout = LAYOUT_ROW if not col_major else (LAYOUT_COL8 if output_layer else LAYOUT_COL128)
+    with torch.cuda.device(x.device):
+        out = torch.empty(packed_shape(layout, nbits, H, W), dtype=torch.int32, device=x.device)
+        _check(lib().qgtc_val2bit(x.data_ptr(), H, W, nbits, int(col_major), int(output_layer), out.data_ptr(), out.numel(), _stream()), "val2bit")
+    return out
+
+
+def bit2val(w: torch.Tensor, nbits: int, H: int, W: int, col_major: bool, output_layer: bool = False) -> torch.Tensor:
+    """QGTC.bit2val (QGTC_host.cpp:244-256)."""
+    _req_cuda(w, torch.int32, "input")
+    with torch.cuda.device(w.device):
+        out = torch.empty((H, W), dtype=torch.int32, device=w.device)
+        _check(lib().qgtc_bit2val(w.data_ptr(), w.numel(), nbits, H, W, int(col_major), int(output_layer), out.data_ptr(), _stream()), "bit2val")
+    return out
+
+
+def bitMM2Bit(x1, x2, M, K, N, bit1, bit2, out_bit, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """QGTC.bitMM2Bit (QGTC_host.cpp:106-122)."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2")
+    with torch.cuda.device(x1.device):
+        out = torch.empty(packed_shape(LAYOUT_ROW, out_bit, M, N), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_bitmm2bit(x1.data_ptr(), x1.numel(), x2.data_ptr(), x2.numel(), M, K, N, bit1, bit2, out_bit,
+                                    out.data_ptr(), out.numel(), engine, flags, _stream()), "bitMM2Bit")
+    return out
+
+
+def bitMM2Bit_col(x1, x2, M, K, N, bit1, bit2, out_bit, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """QGTC.bitMM2Bit_col (QGTC_host.cpp:185-201); flags=FLAG_COL_REF_QUIRK for the shipped kernel's bytes."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2")
+    with torch.cuda.device(x1.device):
+        out = torch.empty(packed_shape(LAYOUT_COL128, out_bit, M, N), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_bitmm2bit_col(x1.data_ptr(), x1.numel(), x2.data_ptr(), x2.numel(), M, K, N, bit1, bit2, out_bit,
+                                        out.data_ptr(), out.numel(), engine, flags, _stream()), "bitMM2Bit_col")
+    return out
+
+
+def bitMM2Int(x1, x2, M, K, N, bit1, bit2, pad_128=False, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """QGTC.bitMM2Int (QGTC_host.cpp:207-223)."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2")
+    with torch.cuda.device(x1.device):
+        out = torch.empty((M, N), dtype=torch.float32, device=x1.device)
+        _check(lib().qgtc_bitmm2int(x1.data_ptr(), x1.numel(), x2.data_ptr(), x2.numel(), M, K, N, bit1, bit2, int(bool(pad_128)),
+                                    out.data_ptr(), out.numel(), engine, flags, _stream()), "bitMM2Int")
+    return out
+
+
+def tile_counts(x1, M, K, N, bit1, bit2) -> tuple[int, int]:
+    """(counter_global, counter) increments of bitMM2Bit_base_cnt / _zerojump_cnt (QGTC_device.cu:272-373)."""
+    _req_cuda(x1, torch.int32, "bit_X1")
+    t, z = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    with torch.cuda.device(x1.device):
+        _check(lib().qgtc_tile_counts(x1.data_ptr(), x1.numel(), M, K, N, bit1, bit2, ctypes.byref(t), ctypes.byref(z), _stream()), "tile_counts")
+    return int(t.value), int(z.value)
+
+
+def bitMM2Bit_batched(x1, x2, count, M, K, N, bit1, bit2, out_bit, out=None, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """`count` independent problems in one launch.  x1: [count, words1], x2: [count, words2] (or a
+    single problem's words to alias it for every problem); returns [count, words_out]."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2")
+    w1, w2, wo = packed_words(LAYOUT_ROW, bit1, M, K), packed_words(LAYOUT_COL128, bit2, K, N), packed_words(LAYOUT_ROW, out_bit, M, N)
+    s1 = 0 if x1.numel() == w1 else w1
+    s2 = 0 if x2.numel() == w2 else w2
+    if (s1 and x1.numel() != count * w1) or (s2 and x2.numel() != count * w2):
+        raise QgtcError("batched operands must hold `count` well-formed problems")
+    with torch.cuda.device(x1.device):
+        if out is None:
+            out = torch.empty((count, wo), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_bitmm2bit_batched(x1.data_ptr(), s1, x2.data_ptr(), s2, count, M, K, N, bit1, bit2, out_bit,
+                                            out.data_ptr(), wo if out.numel() >= count * wo else 0, engine, flags, _stream()), "bitMM2Bit_batched")
+    return out
+
+
+def bitMM2Bit_host(x1_host: torch.Tensor, x2_host: torch.Tensor, M, K, N, bit1, bit2, out_bit, out_host=None,
+                   engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """Host-buffer entry point (pinned CPU int32 tensors in, CPU tensor out): H2D + GEMM + D2H + sync."""
+    for t, n in ((x1_host, "bit_X1"), (x2_host, "bit_X2")):
+        if t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous():
+            raise QgtcError("%s must be a contiguous int32 CPU tensor" % n)
+    if out_host is None:
+        out_host = torch.empty(packed_shape(LAYOUT_ROW, out_bit, M, N), dtype=torch.int32).pin_memory()
+    _check(lib().qgtc_bitmm2bit_host(x1_host.data_ptr(), x1_host.numel(), x2_host.data_ptr(), x2_host.numel(), M, K, N,
+                                     bit1, bit2, out_bit, out_host.data_ptr(), out_host.numel(), engine, flags, _stream()), "bitMM2Bit_host")
+    return out_host

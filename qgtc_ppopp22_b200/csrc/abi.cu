@@ -1,0 +1,278 @@
+// extern "C" entry points of libqgtc_b200.so (declared in include/qgtc_b200.h).
+// Argument validation, launch selection and error reporting only; the kernels live in
+// pack.cu, gemm_mma.cu and gemm_tc05.cu.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gemm_common.cuh"
+
+namespace qgtc {
+
+// kernels (other translation units)
+int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st);
+int launch_bit2val(const uint32_t* in, size_t in_words, int nbits, int H, int W, int col_major, int* out, cudaStream_t st);
+int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K, int bit1, unsigned long long* nz_dev, cudaStream_t st);
+int launch_gemm_mma(const GemmArgs& a, int epi, cudaStream_t st);
+int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st);   // QGTC_ERR_UNSUPPORTED when the shape does not qualify
+bool tc05_supports(const GemmArgs& a, int epi);
+
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local char g_cuda_err[256] = "";
+
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int record_cuda_error(cudaError_t e, const char* where) {
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return QGTC_ERR_CUDA;
+}
+
+int check_launch(const char* where) {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QGTC_OK : record_cuda_error(e, where);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool bits_ok(int b) { return b >= 1 && b <= 8; }
+
+static int check_device() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached_rc = QGTC_ERR_NO_DEVICE;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return QGTC_ERR_NO_DEVICE; }
+    if (dev == cached_dev) return cached_rc;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return QGTC_ERR_NO_DEVICE; }
+    cached_dev = dev;
+    cached_rc = (major == 10) ? QGTC_OK : QGTC_ERR_NO_DEVICE;  // the cubin is sm_100a only
+    return cached_rc;
+}
+
+static int fill_gemm_args(GemmArgs& a, const int32_t* x1, size_t x1_words, const int32_t* x2, size_t x2_words,
+                          int M, int K, int N, int bit1, int bit2, int out_bit, bool pad128, void* out, unsigned flags) {
+    if (!x1 || !x2 || !out || M <= 0 || K <= 0 || N <= 0) return QGTC_ERR_INVALID_ARG;
+    if (!bits_ok(bit1) || !bits_ok(bit2) || !bits_ok(out_bit)) return QGTC_ERR_UNSUPPORTED;
+    if (!aligned16(x1) || !aligned16(x2) || !aligned16(out)) return QGTC_ERR_ALIGNMENT;
+    if ((long long)p8(M) * s128(K) * 4 * 8 > (1ll << 40) || (long long)p128(N) * s128(K) * 4 * 8 > (1ll << 40)) return QGTC_ERR_UNSUPPORTED;
+    std::memset(&a, 0, sizeof(a));
+    a.x1 = reinterpret_cast<const uint32_t*>(x1);
+    a.x2 = reinterpret_cast<const uint32_t*>(x2);
+    a.out = out;
+    a.x1_words = x1_words;
+    a.x2_words = x2_words;
+    a.M = M; a.K = K; a.N = N;
+    a.bit1 = bit1; a.bit2 = bit2; a.out_bit = out_bit;
+    a.gdk = s128(K);
+    a.count = 1;
+    a.act_offset = (unsigned long long)p8(M) * a.gdk * 4;
+    a.w_offset = (unsigned long long)a.gdk * 4 * (pad128 ? p128(N) : p8(N));
+    a.flags = flags;
+    return QGTC_OK;
+}
+
+static int run_gemm(const GemmArgs& a, int epi, int engine, cudaStream_t st) {
+    if (engine == QGTC_ENGINE_TCGEN05) return launch_gemm_tc05(a, epi, st);
+    if (engine == QGTC_ENGINE_AUTO && tc05_supports(a, epi)) return launch_gemm_tc05(a, epi, st);
+    if (engine == QGTC_ENGINE_AUTO || engine == QGTC_ENGINE_MMA_SYNC) return launch_gemm_mma(a, epi, st);
+    return QGTC_ERR_INVALID_ARG;
+}
+
+// library-owned scratch for the host-buffer entry point and the counters
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int dev = -1;
+};
+static std::mutex g_scratch_mu;
+static Scratch g_scratch;
+static int scratch_reserve(size_t bytes, void** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_scratch.dev != dev || g_scratch.bytes < bytes) {
+        if (g_scratch.p && g_scratch.dev == dev) cudaFree(g_scratch.p);
+        g_scratch = Scratch{};
+        const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        const cudaError_t e = cudaMalloc(&g_scratch.p, want);
+        if (e != cudaSuccess) { g_scratch = Scratch{}; return record_cuda_error(e, "cudaMalloc(scratch)"); }
+        g_scratch.bytes = want;
+        g_scratch.dev = dev;
+    }
+    *out = g_scratch.p;
+    return QGTC_OK;
+}
+
+}  // namespace qgtc
+
+using namespace qgtc;
+
+extern "C" {
+
+int qgtc_abi_version(void) { return QGTC_B200_ABI_VERSION; }
+
+const char* qgtc_strerror(int status) {
+    switch (status) {
+        case QGTC_OK: return "ok";
+        case QGTC_ERR_INVALID_ARG: return "invalid argument (null pointer, non-positive dimension or bad enum)";
+        case QGTC_ERR_UNSUPPORTED: return "unsupported (bit width outside [1,8] or problem too large)";
+        case QGTC_ERR_ALIGNMENT: return "packed buffers must be 16-byte aligned";
+        case QGTC_ERR_SIZE: return "output buffer too small";
+        case QGTC_ERR_CUDA: return "CUDA error (see qgtc_last_cuda_error)";
+        case QGTC_ERR_NO_DEVICE: return "no sm_100 (B200) device is current";
+    }
+    return "unknown status";
+}
+
+const char* qgtc_last_cuda_error(void) { return g_cuda_err; }
+
+size_t qgtc_packed_words(int layout, int bits, int H, int W) {
+    if (bits <= 0 || H <= 0 || W <= 0) return 0;
+    switch (layout) {
+        case QGTC_LAYOUT_ROW: return (size_t)bits * p8(H) * s128(W) * 4;
+        case QGTC_LAYOUT_COL128: return (size_t)bits * s128(H) * 4 * p128(W);
+        case QGTC_LAYOUT_COL8: return (size_t)bits * s128(H) * 4 * p8(W);
+    }
+    return 0;
+}
+
+void qgtc_packed_shape(int layout, int bits, int H, int W, int64_t* rows, int64_t* cols) {
+    int64_t r = 0, c = 0;
+    switch (layout) {
+        case QGTC_LAYOUT_ROW: r = (int64_t)bits * p8(H); c = (int64_t)s128(W) * 4; break;
+        case QGTC_LAYOUT_COL128: r = (int64_t)bits * s128(H) * 4; c = p128(W); break;
+        case QGTC_LAYOUT_COL8: r = (int64_t)bits * s128(H) * 4; c = p8(W); break;
+    }
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+}
+
+int qgtc_val2bit(const float* in_dev, int H, int W, int nbits, int col_major, int output_layer,
+                 int32_t* out_dev, size_t out_words, void* stream) {
+    if (!in_dev || !out_dev || H <= 0 || W <= 0) return QGTC_ERR_INVALID_ARG;
+    if (!bits_ok(nbits)) return QGTC_ERR_UNSUPPORTED;
+    if (!aligned16(out_dev)) return QGTC_ERR_ALIGNMENT;
+    const int layout = !col_major ? QGTC_LAYOUT_ROW : (output_layer ? QGTC_LAYOUT_COL8 : QGTC_LAYOUT_COL128);
+    const size_t need = qgtc_packed_words(layout, nbits, H, W);
+    if (out_words < need) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    return launch_val2bit(in_dev, H, W, nbits, layout, reinterpret_cast<uint32_t*>(out_dev), need, (cudaStream_t)stream);
+}
+
+int qgtc_bit2val(const int32_t* in_dev, size_t in_words, int nbits, int H, int W, int col_major,
+                 int output_layer, int32_t* out_dev, void* stream) {
+    (void)output_layer;  // both column-major variants are read with the C128 formula (QGTC_device.cu:157,173)
+    if (!in_dev || !out_dev || H <= 0 || W <= 0) return QGTC_ERR_INVALID_ARG;
+    if (nbits < 1 || nbits > 31) return QGTC_ERR_UNSUPPORTED;
+    if (int rc = check_device()) return rc;
+    return launch_bit2val(reinterpret_cast<const uint32_t*>(in_dev), in_words, nbits, H, W, col_major ? 1 : 0, out_dev, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2bit(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev, size_t x2_words,
+                   int M, int K, int N, int bit1, int bit2, int out_bit,
+                   int32_t* out_dev, size_t out_words, int engine, unsigned flags, void* stream) {
+    GemmArgs a;
+    if (int rc = fill_gemm_args(a, x1_dev, x1_words, x2_dev, x2_words, M, K, N, bit1, bit2, out_bit, true, out_dev, flags)) return rc;
+    if (out_words < qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N)) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    return run_gemm(a, kEpiBitsRow, engine, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2bit_col(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev, size_t x2_words,
+                       int M, int K, int N, int bit1, int bit2, int out_bit,
+                       int32_t* out_dev, size_t out_words, int engine, unsigned flags, void* stream) {
+    GemmArgs a;
+    if (int rc = fill_gemm_args(a, x1_dev, x1_words, x2_dev, x2_words, M, K, N, bit1, bit2, out_bit, true, out_dev, flags)) return rc;
+    const size_t need = qgtc_packed_words(QGTC_LAYOUT_COL128, out_bit, M, N);
+    if (out_words < need) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    // the column-major image has pad words no tile owns: clear it first (off the benchmark path)
+    const cudaError_t e = cudaMemsetAsync(out_dev, 0, need * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(bitmm2bit_col)");
+    (void)engine;  // only the general engine implements the column-major epilogues
+    return launch_gemm_mma(a, (flags & QGTC_FLAG_COL_REF_QUIRK) ? kEpiBitsColQuirk : kEpiBitsCol, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2int(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev, size_t x2_words,
+                   int M, int K, int N, int bit1, int bit2, int pad128,
+                   float* out_dev, size_t out_elems, int engine, unsigned flags, void* stream) {
+    GemmArgs a;
+    if (int rc = fill_gemm_args(a, x1_dev, x1_words, x2_dev, x2_words, M, K, N, bit1, bit2, 1, pad128 != 0, out_dev, flags)) return rc;
+    if (out_elems < (size_t)M * N) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    return run_gemm(a, kEpiFloat, engine, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2bit_batched(const int32_t* x1_dev, size_t x1_stride_words, const int32_t* x2_dev,
+                           size_t x2_stride_words, int count, int M, int K, int N, int bit1, int bit2,
+                           int out_bit, int32_t* out_dev, size_t out_stride_words, int engine,
+                           unsigned flags, void* stream) {
+    if (count <= 0 || count > 65535) return QGTC_ERR_INVALID_ARG;
+    GemmArgs a;
+    const size_t need1 = qgtc_packed_words(QGTC_LAYOUT_ROW, bit1, M, K);
+    const size_t need2 = qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N);
+    const size_t need_o = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
+    if (int rc = fill_gemm_args(a, x1_dev, need1, x2_dev, need2, M, K, N, bit1, bit2, out_bit, true, out_dev, flags)) return rc;
+    if ((x1_stride_words & 3) || (x2_stride_words & 3) || (out_stride_words & 3)) return QGTC_ERR_ALIGNMENT;
+    if (out_stride_words && out_stride_words < need_o) return QGTC_ERR_SIZE;
+    if ((x1_stride_words && x1_stride_words < need1) || (x2_stride_words && x2_stride_words < need2)) return QGTC_ERR_SIZE;
+    a.count = count;
+    a.x1_bstride = x1_stride_words;
+    a.x2_bstride = x2_stride_words;
+    a.out_bstride = out_stride_words;
+    if (int rc = check_device()) return rc;
+    return run_gemm(a, kEpiBitsRow, engine, (cudaStream_t)stream);
+}
+
+int qgtc_tile_counts(const int32_t* x1_dev, size_t x1_words, int M, int K, int N, int bit1, int bit2,
+                     uint64_t* total_host, uint64_t* nonzero_host, void* stream) {
+    if (!x1_dev || !total_host || !nonzero_host || M <= 0 || K <= 0 || N <= 0 || bit1 < 1 || bit2 < 1) return QGTC_ERR_INVALID_ARG;
+    if (!aligned16(x1_dev)) return QGTC_ERR_ALIGNMENT;
+    if (int rc = check_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    void* scratch = nullptr;
+    if (int rc = scratch_reserve(sizeof(unsigned long long), &scratch)) return rc;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(tile_counts)");
+    if (int rc = launch_count_nonzero_tiles(reinterpret_cast<const uint32_t*>(x1_dev), x1_words, M, K, bit1,
+                                            reinterpret_cast<unsigned long long*>(scratch), st)) return rc;
+    unsigned long long nz = 0;
+    e = cudaMemcpyAsync(&nz, scratch, sizeof(nz), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return record_cuda_error(e, "tile_counts readback");
+    // every lane of every warp counts (reference kernel.h:452,587): x32, per column tile, per plane pair
+    *total_host = 32ull * s8(M) * s8(N) * bit1 * bit2 * s128(K);
+    *nonzero_host = 32ull * s8(N) * bit2 * nz;
+    return QGTC_OK;
+}
+
+int qgtc_bitmm2bit_host(const int32_t* x1_host, size_t x1_words, const int32_t* x2_host, size_t x2_words,
+                        int M, int K, int N, int bit1, int bit2, int out_bit,
+                        int32_t* out_host, size_t out_words, int engine, unsigned flags, void* stream) {
+    if (!x1_host || !x2_host || !out_host) return QGTC_ERR_INVALID_ARG;
+    const size_t need_o = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
+    if (need_o == 0) return QGTC_ERR_INVALID_ARG;
+    if (out_words < need_o) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    auto up = [](size_t w) { return (w * 4 + 255) & ~(size_t)255; };
+    void* base = nullptr;
+    if (int rc = scratch_reserve(up(x1_words) + up(x2_words) + up(need_o), &base)) return rc;
+    char* d1 = reinterpret_cast<char*>(base);
+    char* d2 = d1 + up(x1_words);
+    char* d3 = d2 + up(x2_words);
+    cudaError_t e = cudaMemcpyAsync(d1, x1_host, x1_words * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d2, x2_host, x2_words * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "H2D(bitmm2bit_host)");
+    if (int rc = qgtc_bitmm2bit(reinterpret_cast<int32_t*>(d1), x1_words, reinterpret_cast<int32_t*>(d2), x2_words, M, K, N,
+                                bit1, bit2, out_bit, reinterpret_cast<int32_t*>(d3), need_o, engine, flags, stream)) return rc;
+    e = cudaMemcpyAsync(out_host, d3, need_o * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return record_cuda_error(e, "D2H(bitmm2bit_host)");
+    return QGTC_OK;
+}
+
+uint64_t qgtc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// PyTorch extension `QGTC`: the reference's Python op surface (QGTC_module/QGTC_host.cpp:259-271)
+// as a thin pybind11 layer over the C ABI in include/qgtc_b200.h.
+//
+// Same eight functions, same positional-only signatures, same returned shapes and dtypes
+// (QGTC_device.cu:83,97,115,223,456,507).  Differences, all deliberate:
+//   * outputs are allocated on the tensor's device (torch::empty) and the work is enqueued on the
+//     current PyTorch stream; no host synchronisation, no cudaGetDeviceProperties per call;
+//   * dtype / size mistakes raise RuntimeError instead of being undefined behaviour, CUDA errors
+//     raise instead of exit(-1);
+//   * bit2val does not print the tensor;  bitMM2Bit_col implements the intended column-major
+//     output (set QGTC_COL_REF_QUIRK=1 in the environment for the shipped kernel's exact bytes).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "qgtc_b200.h"
+
+namespace {
+
+#define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+#define CHECK_CONTIGUOUS(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define CHECK_INPUT(x) \
+    CHECK_CUDA(x);     \
+    CHECK_CONTIGUOUS(x)
+
+void check_status(int rc, const char* op) {
+    if (rc == QGTC_OK) return;
+    if (rc == QGTC_ERR_CUDA) TORCH_CHECK(false, "QGTC.", op, ": ", qgtc_strerror(rc), ": ", qgtc_last_cuda_error());
+    TORCH_CHECK(false, "QGTC.", op, ": ", qgtc_strerror(rc));
+}
+
+void* current_stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
+
+torch::Tensor packed_input(const torch::Tensor& t, const char* name) {
+    TORCH_CHECK(t.scalar_type() == torch::kInt32, name, " must be an int32 packed tensor");
+    if ((reinterpret_cast<uintptr_t>(t.data_ptr()) & 15u) != 0) return t.clone();  // re-align odd views
+    return t;
+}
+
+int engine_from_env() {
+    static const int e = [] {
+        const char* s = std::getenv("QGTC_ENGINE");
+        if (!s) return (int)QGTC_ENGINE_AUTO;
+        if (!std::strcmp(s, "mma")) return (int)QGTC_ENGINE_MMA_SYNC;
+        if (!std::strcmp(s, "tcgen05")) return (int)QGTC_ENGINE_TCGEN05;
+        return (int)QGTC_ENGINE_AUTO;
+    }();
+    return e;
+}
+
+unsigned flags_from_env() {
+    static const unsigned f = [] {
+        unsigned v = 0;
+        const char* z = std::getenv("QGTC_NO_ZERO_JUMP");
+        if (z && z[0] == '1') v |= QGTC_FLAG_NO_ZERO_JUMP;
+        return v;
+    }();
+    return f;
+}
+
+// cumulative counters, like the reference's __device__ globals (kernel.h:13-14), printed as %d
+unsigned long long g_counter = 0, g_counter_global = 0;
+
+torch::Tensor val2bit(torch::Tensor input, const int nbits, const bool col_major, const bool output_layer) {
+    CHECK_INPUT(input);
+    TORCH_CHECK(input.dim() == 2, "input must be 2-D");
+    TORCH_CHECK(input.scalar_type() == torch::kFloat32, "input must be float32");
+    const c10::cuda::CUDAGuard guard(input.device());
+    const int H = (int)input.size(0), W = (int)input.size(1);
+    const int layout = !col_major ? QGTC_LAYOUT_ROW : (output_layer ? QGTC_LAYOUT_COL8 : QGTC_LAYOUT_COL128);
+    TORCH_CHECK(nbits >= 1 && nbits <= 8, "nbits must be in [1, 8]");
+    TORCH_CHECK(H > 0 && W > 0, "input must be non-empty");
+    int64_t r = 0, c = 0;
+    qgtc_packed_shape(layout, nbits, H, W, &r, &c);
+    auto out = torch::empty({r, c}, input.options().dtype(torch::kInt32));
+    check_status(qgtc_val2bit(input.data_ptr<float>(), H, W, nbits, col_major, output_layer, out.data_ptr<int32_t>(),
+                              (size_t)out.numel(), current_stream()), "val2bit");
+    return out;
+}
+
+torch::Tensor bit2val(torch::Tensor input, const int nbits, const int height, const int width, const bool col_major,
+                      const bool output_layer) {
+    CHECK_INPUT(input);
+    const c10::cuda::CUDAGuard guard(input.device());
+    auto in = packed_input(input, "input");
+    TORCH_CHECK(height > 0 && width > 0, "height and width must be positive");
+    auto out = torch::empty({height, width}, input.options().dtype(torch::kInt32));
+    check_status(qgtc_bit2val(in.data_ptr<int32_t>(), (size_t)in.numel(), nbits, height, width, col_major, output_layer,
+                              out.data_ptr<int32_t>(), current_stream()), "bit2val");
+    return out;
+}
+
+torch::Tensor mm2bit_impl(const torch::Tensor& X1, const torch::Tensor& X2, int M, int K, int N, int bit1, int bit2, int out_bit,
+                          const char* op) {
+    CHECK_INPUT(X1);
+    CHECK_INPUT(X2);
+    const c10::cuda::CUDAGuard guard(X1.device());
+    auto a = packed_input(X1, "bit_X1"), b = packed_input(X2, "bit_X2");
+    TORCH_CHECK(M > 0 && K > 0 && N > 0, "dimensions must be positive");
+    int64_t r = 0, c = 0;
+    qgtc_packed_shape(QGTC_LAYOUT_ROW, out_bit, M, N, &r, &c);
+    auto out = torch::empty({r, c}, X1.options().dtype(torch::kInt32));
+    check_status(qgtc_bitmm2bit(a.data_ptr<int32_t>(), (size_t)a.numel(), b.data_ptr<int32_t>(), (size_t)b.numel(), M, K, N, bit1,
+                                bit2, out_bit, out.data_ptr<int32_t>(), (size_t)out.numel(), engine_from_env(), flags_from_env(),
+                                current_stream()), op);
+    return out;
+}
+
+torch::Tensor bitMM2Bit(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width, const int X2_width,
+                        const int bit1, const int bit2, const int output_bit) {
+    return mm2bit_impl(bit_X1, bit_X2, X1_height, X1_width, X2_width, bit1, bit2, output_bit, "bitMM2Bit");
+}
+
+// 200 repetitions timed with CUDA events and the reference's stdout line (QGTC_device.cu:379-434).
+// The repetitions are one batched launch whose 200 problems alias the same operands and output:
+// the same work as the reference's 200 back-to-back launches without 200 launch latencies.
+torch::Tensor bitMM2Bit_profile(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width,
+                                const int X2_width, const int bit1, const int bit2, const int output_bit) {
+    CHECK_INPUT(bit_X1);
+    CHECK_INPUT(bit_X2);
+    const c10::cuda::CUDAGuard guard(bit_X1.device());
+    auto a = packed_input(bit_X1, "bit_X1"), b = packed_input(bit_X2, "bit_X2");
+    const int M = X1_height, K = X1_width, N = X2_width, PROF = 200;
+    TORCH_CHECK(M > 0 && K > 0 && N > 0, "dimensions must be positive");
+    TORCH_CHECK((size_t)a.numel() >= qgtc_packed_words(QGTC_LAYOUT_ROW, bit1, M, K) &&
+                    (size_t)b.numel() >= qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N),
+                "bitMM2Bit_profile needs well-formed operands (R(bit1,M,K) and C128(bit2,K,N))");
+    int64_t r = 0, c = 0;
+    qgtc_packed_shape(QGTC_LAYOUT_ROW, output_bit, M, N, &r, &c);
+    auto out = torch::empty({r, c}, bit_X1.options().dtype(torch::kInt32));
+    cudaStream_t st = (cudaStream_t)current_stream();
+    auto run = [&](int count) {
+        check_status(qgtc_bitmm2bit_batched(a.data_ptr<int32_t>(), 0, b.data_ptr<int32_t>(), 0, count, M, K, N, bit1, bit2,
+                                            output_bit, out.data_ptr<int32_t>(), 0, engine_from_env(), flags_from_env(), st),
+                     "bitMM2Bit_profile");
+    };
+    run(2);  // warm-up
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    run(PROF);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    std::printf("X1_height %d, X1_width: %d, X2_width: %d, TFLOPs: %.3f\n", M, K, N,
+                2.0 * M * K * N * PROF / (ms / 1e3) / 1e12);
+    std::fflush(stdout);
+    return out;
+}
+
+void add_counts(const torch::Tensor& X1, int M, int K, int N, int bit1, int bit2) {
+    auto a = packed_input(X1, "bit_X1");
+    uint64_t total = 0, nz = 0;
+    check_status(qgtc_tile_counts(a.data_ptr<int32_t>(), (size_t)a.numel(), M, K, N, bit1, bit2, &total, &nz, current_stream()),
+                 "tile_counts");
+    g_counter_global += total;
+    g_counter += nz;
+}
+
+torch::Tensor bitMM2Bit_base_cnt(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width,
+                                 const int X2_width, const int bit1, const int bit2, const int output_bit) {
+    auto out = mm2bit_impl(bit_X1, bit_X2, X1_height, X1_width, X2_width, bit1, bit2, output_bit, "bitMM2Bit_base_cnt");
+    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2);
+    std::printf("counter_global: %d\n", (int)g_counter_global);  // low 32 bits, as the reference's %d (kernel.h:27)
+    std::fflush(stdout);
+    return out;
+}
+
+torch::Tensor bitMM2Bit_zerojump_cnt(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width,
+                                     const int X2_width, const int bit1, const int bit2, const int output_bit) {
+    auto out = mm2bit_impl(bit_X1, bit_X2, X1_height, X1_width, X2_width, bit1, bit2, output_bit, "bitMM2Bit_zerojump_cnt");
+    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2);
+    std::printf("counter: %d\n", (int)g_counter);
+    std::fflush(stdout);
+    return out;
+}
+
+torch::Tensor bitMM2Bit_col(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width, const int X2_width,
+                            const int bit1, const int bit2, const int output_bit) {
+    CHECK_INPUT(bit_X1);
+    CHECK_INPUT(bit_X2);
+    const c10::cuda::CUDAGuard guard(bit_X1.device());
+    auto a = packed_input(bit_X1, "bit_X1"), b = packed_input(bit_X2, "bit_X2");
+    TORCH_CHECK(X1_height > 0 && X1_width > 0 && X2_width > 0, "dimensions must be positive");
+    int64_t r = 0, c = 0;
+    qgtc_packed_shape(QGTC_LAYOUT_COL128, output_bit, X1_height, X2_width, &r, &c);
+    auto out = torch::empty({r, c}, bit_X1.options().dtype(torch::kInt32));
+    const char* q = std::getenv("QGTC_COL_REF_QUIRK");
+    const unsigned flags = flags_from_env() | ((q && q[0] == '1') ? QGTC_FLAG_COL_REF_QUIRK : 0u);
+    check_status(qgtc_bitmm2bit_col(a.data_ptr<int32_t>(), (size_t)a.numel(), b.data_ptr<int32_t>(), (size_t)b.numel(), X1_height,
+                                    X1_width, X2_width, bit1, bit2, output_bit, out.data_ptr<int32_t>(), (size_t)out.numel(),
+                                    engine_from_env(), flags, current_stream()), "bitMM2Bit_col");
+    return out;
+}
+
+torch::Tensor bitMM2Int(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width, const int X2_width,
+                        const int bit1, const int bit2, const bool pad_128) {
+    CHECK_INPUT(bit_X1);
+    CHECK_INPUT(bit_X2);
+    const c10::cuda::CUDAGuard guard(bit_X1.device());
+    auto a = packed_input(bit_X1, "bit_X1"), b = packed_input(bit_X2, "bit_X2");
+    TORCH_CHECK(X1_height > 0 && X1_width > 0 && X2_width > 0, "dimensions must be positive");
+    auto out = torch::empty({X1_height, X2_width}, bit_X1.options().dtype(torch::kFloat32));
+    check_status(qgtc_bitmm2int(a.data_ptr<int32_t>(), (size_t)a.numel(), b.data_ptr<int32_t>(), (size_t)b.numel(), X1_height,
+                                X1_width, X2_width, bit1, bit2, pad_128 ? 1 : 0, out.data_ptr<float>(), (size_t)out.numel(),
+                                engine_from_env(), flags_from_env(), current_stream()), "bitMM2Int");
+    return out;
+}
+
+}  // namespace
+
+// Same names, order and docstrings as the reference binding (QGTC_host.cpp:259-271); no py::arg,
+// so every argument is positional and required, as there.
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("val2bit", &val2bit, "quantize a [ int32 --> bit ] tensor (CUDA)");
+    m.def("bit2val", &bit2val, "quantize a [ bit --> int32 ] tensor (CUDA)");
+    m.def("bitMM2Bit", &bitMM2Bit, "QGTC [ bit_A x bit_B --> bit_C ] forward (CUDA)");
+    m.def("bitMM2Bit_profile", &bitMM2Bit_profile, "QGTC [ bit_A x bit_B --> bit_C ] forward (CUDA) for profiling (200)");
+    m.def("bitMM2Bit_base_cnt", &bitMM2Bit_base_cnt, "QGTC [ bit_A x bit_B --> bit_C ] forward (CUDA) base count");
+    m.def("bitMM2Bit_zerojump_cnt", &bitMM2Bit_zerojump_cnt, "QGTC [ bit_A x bit_B --> bit_C ] forward (CUDA) zero jump count");
+    m.def("bitMM2Bit_col", &bitMM2Bit_col, "QGTC [ bit_A x bit_B --> bit_C (column major) ] forward (CUDA)");
+    m.def("bitMM2Int", &bitMM2Int, "QGTC [ bit_A x bit_B --> float32 ] forward (CUDA)");
+    m.attr("__backend__") = "qgtc_b200";
+}
