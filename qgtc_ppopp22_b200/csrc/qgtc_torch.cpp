@@ -156,19 +156,20 @@ torch::Tensor bitMM2Bit_profile(torch::Tensor bit_X1, torch::Tensor bit_X2, cons
     return out;
 }
 
-void add_counts(const torch::Tensor& X1, int M, int K, int N, int bit1, int bit2) {
+// base_cnt only advances counter_global (kernel.h:452), zerojump_cnt only counter (kernel.h:587)
+void add_counts(const torch::Tensor& X1, int M, int K, int N, int bit1, int bit2, bool global_counter) {
     auto a = packed_input(X1, "bit_X1");
     uint64_t total = 0, nz = 0;
     check_status(qgtc_tile_counts(a.data_ptr<int32_t>(), (size_t)a.numel(), M, K, N, bit1, bit2, &total, &nz, current_stream()),
                  "tile_counts");
-    g_counter_global += total;
-    g_counter += nz;
+    if (global_counter) g_counter_global += total;
+    else g_counter += nz;
 }
 
 torch::Tensor bitMM2Bit_base_cnt(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width,
                                  const int X2_width, const int bit1, const int bit2, const int output_bit) {
     auto out = mm2bit_impl(bit_X1, bit_X2, X1_height, X1_width, X2_width, bit1, bit2, output_bit, "bitMM2Bit_base_cnt");
-    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2);
+    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2, true);
     std::printf("counter_global: %d\n", (int)g_counter_global);  // low 32 bits, as the reference's %d (kernel.h:27)
     std::fflush(stdout);
     return out;
@@ -177,7 +178,7 @@ torch::Tensor bitMM2Bit_base_cnt(torch::Tensor bit_X1, torch::Tensor bit_X2, con
 torch::Tensor bitMM2Bit_zerojump_cnt(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1_height, const int X1_width,
                                      const int X2_width, const int bit1, const int bit2, const int output_bit) {
     auto out = mm2bit_impl(bit_X1, bit_X2, X1_height, X1_width, X2_width, bit1, bit2, output_bit, "bitMM2Bit_zerojump_cnt");
-    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2);
+    add_counts(bit_X1, X1_height, X1_width, X2_width, bit1, bit2, false);
     std::printf("counter: %d\n", (int)g_counter);
     std::fflush(stdout);
     return out;
