@@ -1,0 +1,91 @@
+"""GPU parity tests of the tcgen05 engine (engine=ENGINE_TCGEN05 forced): tcgen05.mma kind::i8 with the
+adjacency expanded into TMEM, against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import rand_adj, rand_features
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from qgtc_ppopp22_b200 import capi as c
+    c.lib()
+    return c
+
+
+def dev_words(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def host_u32(t):
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+CASES = [
+    (128, 128, 16, 1, 1), (128, 256, 64, 2, 2), (8, 128, 8, 1, 1), (3, 3, 3, 2, 2), (300, 1000, 40, 2, 2),
+    (759, 759, 16, 2, 2), (515, 515, 29, 2, 2), (2258, 2258, 128, 2, 2), (1000, 3000, 121, 4, 4),
+    (257, 129, 200, 8, 8), (130, 513, 256, 3, 5), (1024, 1024, 32, 4, 4), (2048, 2048, 64, 8, 8), (640, 4096, 48, 5, 3),
+]
+
+
+@pytest.mark.parametrize("M,K,N,b2,ob", CASES)
+def test_tc05_bitmm2bit_and_int(capi, coracle, M, K, N, b2, ob):
+    rng = np.random.default_rng(M + K + N)
+    A = rand_adj(rng, M, K, 0.2, zero_blocks=True)
+    X = rand_features(rng, (K, N), b2)
+    ba, bx, bx8 = coracle.val2bit(A, 1, False, False), coracle.val2bit(X, b2, True, False), coracle.val2bit(X, b2, True, True)
+    da, dx = dev_words(ba), dev_words(bx)
+    E = capi.ENGINE_TCGEN05
+    got = capi.bitMM2Bit(da, dx, M, K, N, 1, b2, ob, engine=E)
+    assert np.array_equal(host_u32(got), coracle.bitMM2Bit(ba, bx, M, K, N, 1, b2, ob))
+    nj = capi.bitMM2Bit(da, dx, M, K, N, 1, b2, ob, engine=E, flags=capi.FLAG_NO_ZERO_JUMP)
+    assert torch.equal(nj, got)
+    gi = capi.bitMM2Int(da, dx, M, K, N, 1, b2, True, engine=E)
+    assert np.array_equal(gi.cpu().numpy(), coracle.bitMM2Int(ba, bx, M, K, N, 1, b2, True))
+    g8 = capi.bitMM2Int(da, dev_words(bx8), M, K, N, 1, b2, False, engine=E)
+    assert np.array_equal(g8.cpu().numpy(), coracle.bitMM2Int(ba, bx8, M, K, N, 1, b2, False))
+    # the two engines agree with each other as well
+    assert torch.equal(capi.bitMM2Bit(da, dx, M, K, N, 1, b2, ob, engine=capi.ENGINE_MMA_SYNC), got)
+
+
+@pytest.mark.parametrize("b", [1, 2, 4, 8])
+def test_tc05_headline_shape(capi, coracle, b):
+    M = K = 4096
+    N = 64
+    rng = np.random.default_rng(40 + b)
+    A = rand_adj(rng, M, K, 0.5 if b != 4 else 0.003, zero_blocks=(b == 2))
+    X = rand_features(rng, (K, N), b)
+    ba, bx = coracle.val2bit(A, 1, False, False), coracle.val2bit(X, b, True, False)
+    got = capi.bitMM2Bit(dev_words(ba), dev_words(bx), M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
+    assert np.array_equal(host_u32(got), coracle.bitMM2Bit(ba, bx, M, K, N, 1, b, b))
+
+
+def test_tc05_raw_memory_operands(capi, coracle):
+    """A row-major product fed into the column-major slot (main_qgtc.py:148): zero-extension applies."""
+    n, h, b = 1500, 16, 2
+    rng = np.random.default_rng(8)
+    A = rand_adj(rng, n, n, 0.01)
+    prev = coracle.val2bit(rand_features(rng, (n, h), b), b, False, False)      # R(b, n, h) used as the B operand
+    ba = coracle.val2bit(A, 1, False, False)
+    got = capi.bitMM2Bit(dev_words(ba), dev_words(prev), n, n, h, 1, b, b, engine=capi.ENGINE_TCGEN05)
+    assert np.array_equal(host_u32(got), coracle.bitMM2Bit(ba, prev, n, n, h, 1, b, b))
+
+
+def test_tc05_batched(capi, coracle):
+    M, K, N, b, cnt = 512, 640, 64, 2, 7
+    rng = np.random.default_rng(12)
+    x1 = np.stack([coracle.val2bit(rand_adj(rng, M, K, 0.05, zero_blocks=(i % 2 == 0)), 1, False, False).reshape(-1) for i in range(cnt)])
+    x2 = np.stack([coracle.val2bit(rand_features(rng, (K, N), b), b, True, False).reshape(-1) for _ in range(cnt)])
+    out = capi.bitMM2Bit_batched(dev_words(x1), dev_words(x2), cnt, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
+    for i in range(cnt):
+        assert np.array_equal(host_u32(out[i]).reshape(-1), coracle.bitMM2Bit(x1[i], x2[i], M, K, N, 1, b, b).reshape(-1)), i
+
+
+def test_tc05_unsupported_shapes_are_refused(capi):
+    a = torch.zeros((2 * 8, 4), dtype=torch.int32, device="cuda")
+    b = torch.zeros((2 * 4, 128), dtype=torch.int32, device="cuda")
+    with pytest.raises(capi.QgtcError, match="unsupported"):
+        capi.bitMM2Bit(a, b, 8, 8, 8, 2, 2, 2, engine=capi.ENGINE_TCGEN05)   # multi-bit A goes to the mma engine
