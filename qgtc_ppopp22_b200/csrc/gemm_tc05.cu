@@ -2,22 +2,29 @@
 //
 // Data flow of one CTA (persistent, one per SM), for a 128-row adjacency tile:
 //
-//   packed 1-bit adjacency rows --cp.async--> smem ring --LDS.128--> registers
-//        --(w >> c) & 0x01010101, 2 ALU ops per 4 bytes--> 32 registers = 128 u8 of one row
-//        --tcgen05.st.32x32b.x32--> TMEM  (the MMA's A operand, one row per TMEM lane)
+//   packed 1-bit adjacency tile  --TMA (cp.async.bulk.tensor, 64B/32B swizzle)--> smem ring
+//        --LDS.128--> registers --(w >> c) & 0x01010101 : 4 bytes per register--> 32 registers
+//        = 128 u8 of one row  --tcgen05.st.32x32b.x32--> TMEM (the MMA's A operand, row = lane)
 //   feature "image" (u8, K-major core matrices, produced once per call by prep_b_kernel)
 //        --cp.async.bulk + mbarrier--> smem stage (the MMA's B operand, no-swizzle descriptor)
 //   tcgen05.mma.cta_group::1.kind::i8  D[tmem] (+)= A[tmem] x B[smem], 4 per 128-bit K chunk
-//   tcgen05.ld --> requantize + pack planes (or float) in registers --> coalesced global stores
+//   tcgen05.ld --> requantize + pack planes (or float) in registers --> global stores
 //
 // The adjacency never exists as bytes in shared or global memory: 1 bit per element is read from
 // HBM, the 8x inflation happens in registers and goes straight to tensor memory.  The K order
 // inside a 32-element step is permuted (byte i of column c is bit c+8i of the packed word) so the
 // expansion is one shift and one mask per register; the feature image uses the same permutation.
 //
-// Warp roles: warps 0-7 adjacency producers, 8-11 epilogue, 12 feature loader, 13 MMA issuer.
-// Zero-tile jumping: a producer warp whose 32 rows x 128 bits are all zero skips the expansion and
-// reports it; if the whole tile chunk is zero the MMA issuer skips its 4 MMAs.
+// A pipeline stage covers `cps` K chunks of 128 bits (cps * NP = 256, so a stage is always 16
+// column-64-equivalent MMAs) to amortise the per-stage barrier round trips.
+// Warp roles: warps 0-7 adjacency expanders (two groups alternating stages), 8-11 epilogue,
+// 12 feature loader, 13 MMA issuer, 14 adjacency TMA loader.
+// Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero skips the expansion and
+// reports it; if the whole 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "gemm_common.cuh"
 
 namespace qgtc {
@@ -28,23 +35,36 @@ constexpr int kProducerWarps = 8;
 constexpr int kEpilogueWarp0 = 8;
 constexpr int kLoaderWarp = 12;
 constexpr int kMmaWarp = 13;
-constexpr int kThreads = 14 * 32;
-constexpr int kADepth = 4;        // cp.async ring depth per producer thread (in its own items)
-constexpr int kMaxStages = 8;
+constexpr int kALoaderWarp = 14;
+constexpr int kThreads = 15 * 32;
+constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
+constexpr int kMaxStages = 4;
+constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
 constexpr int kTmemCols = 512;
 
 struct Tc05Args {
     GemmArgs g;
     const uint8_t* bimg;            // feature image: [count][gdk][NP x 128 B]
-    unsigned long long bimg_gstride;  // bytes per problem
+    unsigned long long bimg_gstride;  // bytes per problem (0 when every problem aliases one feature matrix)
     int NP;                         // padded N (multiple of 16, <= 256)
     int stages;                     // A (TMEM) / B (smem) ring depth
+    int cps;                        // K chunks per stage (1, 2 or 4)
+    int nst;                        // stages per tile = ceil(gdk / cps)
     int dbufs;                      // accumulator buffers (1 or 2)
     int mtiles;                     // 128-row tiles per problem
     int total_tiles;                // count * mtiles
     int epi;
+    int a_batched;                  // 1: the tensor map's third coordinate is the problem index
+    unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
     unsigned int* error_flag;       // device word set by the watchdog
+    unsigned long long* trace;      // optional clock64 trace of CTA 0 (QGTC_TC05_TRACE=1), else null
 };
+constexpr int kTraceItems = 512;    // per role: [item][8] timestamps
+#define QGTC_TRACE(role, item, slot)                                                             \
+    do {                                                                                         \
+        if (T.trace && blockIdx.x == 0 && (item) < kTraceItems)                                  \
+            T.trace[((role) * kTraceItems + (item)) * 8 + (slot)] = (unsigned long long)clock64(); \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -64,18 +84,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  ~2^26 polls is far beyond any legitimate wait.
+// Bounded wait: a protocol bug must not hang the GPU (each failed try_wait has slept up to ~10 ms).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* error_flag, int where) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (++spins > 400u) {
             if (error_flag) atomicExch(error_flag, 0x80000000u | (unsigned)where);
             __trap();
         }
@@ -104,17 +124,40 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (cute::elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// SS form (A from shared memory); only used by a timing experiment
+__device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void cp_async16_ca_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+// 3-D tiled TMA load (cute::SM90_TMA_LOAD_3D): box of the tensor map at element coordinates (c0, c1, c2)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -154,25 +197,38 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
 }
 
 struct SmemLayout {
-    // offsets in bytes from the 128-byte aligned base
-    int b_stage0, b_stage_bytes, a_ring, bars, flags, misc, total;
+    // offsets in bytes from the 1024-byte aligned base
+    int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int NP, int stages) {
+__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps) {
     SmemLayout L;
-    L.b_stage0 = 0;
-    L.b_stage_bytes = NP * 128;
-    L.a_ring = L.b_stage0 + stages * L.b_stage_bytes;
-    L.bars = L.a_ring + kProducerWarps * kADepth * 32 * 16;
-    L.flags = L.bars + (3 * kMaxStages + 4) * 8;
+    L.raw0 = 0;
+    L.raw_slot_bytes = 128 * 16 * cps;                 // 2/4/8 KB, keeps every slot 1024-byte aligned for the swizzle
+    if (L.raw_slot_bytes < 1024) L.raw_slot_bytes = 1024;
+    L.b_stage0 = L.raw0 + kRawSlots * L.raw_slot_bytes;
+    L.b_stage_bytes = cps * NP * 128;
+    L.bars = L.b_stage0 + stages * L.b_stage_bytes;
+    L.flags = L.bars + (2 * kMaxStages + 2 * kRawSlots + 4) * 8;
     L.misc = L.flags + kMaxStages * 8;
     L.total = L.misc + 32;
     return L;
 }
 
-// One (tile, chunk) item of the persistent schedule
-struct Item {
-    int tl;  // CTA-local tile counter
-    int c;   // K chunk
+// Walks a CTA's (tile, chunk) items with a fixed stride, tracking the ring stage and how often it
+// has been used -- all by increments, no divisions in the hot loops.
+struct Cursor {
+    int tl, c, s;
+    uint32_t use;
+    __device__ __forceinline__ void init(int start, int gdk, int S) {
+        tl = 0; c = start; s = start % S; use = 0;
+        while (c >= gdk) { c -= gdk; ++tl; }
+    }
+    __device__ __forceinline__ void advance(int step, int gdk, int S) {   // step <= S
+        c += step;
+        while (c >= gdk) { c -= gdk; ++tl; }
+        s += step;
+        if (s >= S) { s -= S; ++use; }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -209,30 +265,36 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
 // The GEMM kernel
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const GemmArgs& P = T.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NP = T.NP, S = T.stages, gdk = P.gdk;
-    const SmemLayout L = smem_layout(NP, S);
+    const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps, nst = T.nst;
+    const SmemLayout L = smem_layout(NP, S, CPS);
 
+    unsigned char* raw_slots = smem_raw + L.raw0;
     unsigned char* b_stages = smem_raw + L.b_stage0;
-    uint4* a_ring = reinterpret_cast<uint4*>(smem_raw + L.a_ring);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    uint64_t* a_full = bars;                    // [kMaxStages] producers -> MMA      (count 4 warps)
-    uint64_t* b_full = bars + kMaxStages;       // [kMaxStages] bulk copy -> MMA      (count 1 + tx)
-    uint64_t* empty = bars + 2 * kMaxStages;    // [kMaxStages] MMA commit -> producers, loader
-    uint64_t* d_full = bars + 3 * kMaxStages;   // [2] MMA -> epilogue                (count 2: commit + plain arrive)
-    uint64_t* d_empty = d_full + 2;             // [2] epilogue -> MMA                (count 4 warps)
-    volatile unsigned char* flags = smem_raw + L.flags;  // [stage][8]: per producer warp "chunk is non-zero"
+    uint64_t* full = bars;                          // [kMaxStages] 4 expander warps + the bulk copy's expect_tx -> MMA
+    uint64_t* empty = bars + kMaxStages;            // [kMaxStages] MMA commit -> expanders, feature loader
+    uint64_t* raw_full = bars + 2 * kMaxStages;     // [kRawSlots]  adjacency TMA -> expanders
+    uint64_t* raw_empty = raw_full + kRawSlots;     // [kRawSlots]  4 expander warps -> adjacency loader
+    uint64_t* d_full = raw_empty + kRawSlots;       // [2] MMA -> epilogue   (count 2: commit + plain arrive)
+    uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 4 warps)
+    volatile unsigned char* flags = smem_raw + L.flags;  // [stage][8]: per expander warp, bit j = chunk j of the stage is non-zero
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.misc);
     volatile uint32_t* d_valid = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc + 8);  // [2]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
-            mbar_init(&a_full[s], 4);
-            mbar_init(&b_full[s], 1);
+            mbar_init(&full[s], 5);
             mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < kRawSlots; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], 4);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 2);
@@ -240,126 +302,219 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         }
         fence_mbar_init();
     }
+    if (warp == kALoaderWarp && lane == 0) prefetch_tmap(&tmapA);
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int dcols = T.dbufs * NP;  // accumulators first, then the A stages (32 columns each)
+    const int dcols = T.dbufs * NP;       // accumulators first, then the A stages (32 columns per chunk)
+    const int stage_cols = CPS * 32;
 
     const int my_tiles = (T.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long n_items = (long long)my_tiles * gdk;
-    const unsigned long long gdk4 = (unsigned long long)gdk * 4;
-    const int m_lim = p8(P.M);
+    const int n_items = my_tiles * nst;   // launch_gemm_tc05 guarantees this fits 31 bits
     const bool nojump = (P.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
+    // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
+    const bool dbg_no_st = (P.flags & 0x10000u) != 0, dbg_no_mma = (P.flags & 0x20000u) != 0;
+    const bool dbg_no_bulk = (P.flags & 0x40000u) != 0, dbg_no_ldg = (P.flags & 0x80000u) != 0;
+    const bool use_mulhi = (P.flags & 0x100000u) == 0;
 
     if (warp < kProducerWarps) {
-        // ===================== adjacency producers =====================
-        const int q = warp & 3, par = warp >> 2;   // TMEM lane quarter; this warp takes chunks with it % 2 == par
-        const int row_in_tile = 32 * q + lane;
-        uint4* my_ring = a_ring + (warp * kADepth) * 32 + lane;   // slot k at my_ring[k * 32]
-        const long long my_items = (n_items - par + 1) / 2;       // items par, par+2, ...
-
-        auto fetch = [&](long long k) {  // k-th item of this warp
-            if (k < my_items) {
-                const long long it = 2 * k + par;
-                const int tl = (int)(it / gdk), c = (int)(it % gdk);
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int z = tile / T.mtiles, m = (tile % T.mtiles) * 128 + row_in_tile;
-                const uint32_t* base = P.x1 + (unsigned long long)z * P.x1_bstride;
-                const unsigned long long idx = (unsigned long long)m * gdk4 + 4ull * c;
-                int nb = 0;
-                if (m < m_lim && idx < P.x1_words) {
-                    const unsigned long long left = P.x1_words - idx;
-                    nb = left >= 4 ? 16 : (int)left * 4;
-                }
-                cp_async16_ca_zfill(my_ring + (k % kADepth) * 32, nb ? (const void*)(base + idx) : (const void*)base, nb);
-            }
-            cp_async_commit();
-        };
+        // ===================== adjacency expanders =====================
+        const int q = warp & 3, par = warp >> 2;   // TMEM lane quarter; this warp takes the items with it % 2 == par
+        const int row = 32 * q + lane;             // row of the tile == TMEM lane
+        const int my_items = (n_items - par + 1) / 2;
+        // byte offset of logical 16-byte chunk j of this row inside a raw slot, with the TMA swizzle
+        // (Swizzle<log2(cps),4,3>: address bits [4,4+log2 cps) ^= bits [7,7+log2 cps))
+        uint32_t off[kMaxCps];
 #pragma unroll
-        for (int k = 0; k < kADepth; ++k) fetch(k);
-
-        for (long long k = 0; k < my_items; ++k) {
-            const long long it = 2 * k + par;
-            const int s = (int)(it % S);
-            const uint32_t use = (uint32_t)(it / S);
-            cp_async_wait<kADepth - 1>();
-            const uint4 v = my_ring[(k % kADepth) * 32];
-            fetch(k + kADepth);  // refill the slot just read (same thread reads and writes it)
-            const bool nz = nojump || __any_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u);
-            mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // MMA of the previous use of this stage is done
-            tc_fence_after();
-            uint32_t r[32];
-            if (nz) {
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-                    for (int cidx = 0; cidx < 8; ++cidx) r[ks * 8 + cidx] = (w[ks] >> cidx) & 0x01010101u;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            tmem_st32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + s * 32), r);
-            tmem_wait_st();
-            tc_fence_before();
-            if (lane == 0) flags[s * 8 + warp] = nz ? 1 : 0;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[s]);
+        for (int j = 0; j < kMaxCps; ++j) {
+            uint32_t o = (uint32_t)(row * 16 * CPS + 16 * j);
+            o ^= ((o >> 7) & (uint32_t)(CPS - 1)) << 4;
+            off[j] = o;
         }
-        cp_async_wait<0>();
+        // multipliers 2^(32-c): mul.hi gives w >> c on the FMA pipe, leaving only the mask for the ALU pipe
+        uint32_t mult[8];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) mult[c] = T.one << (32 - c);
+        mult[0] = 0;
+
+        int slot = par, s = par;                   // raw ring slot and TMEM/B stage of the current item
+        uint32_t raw_use = 0, use = 0;
+        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)dcols;
+        for (int k = 0; k < my_items; ++k) {
+            const bool tr = (warp == 0 && lane == 0);
+            if (tr) QGTC_TRACE(0, k, 0);
+            uint4 v[kMaxCps];
+            if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7);
+            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes;
+#pragma unroll
+            for (int j = 0; j < kMaxCps; ++j) v[j] = (j < CPS) ? *reinterpret_cast<const uint4*>(src + off[j]) : make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[slot]);       // the slot can be refilled while we expand
+            if (tr) QGTC_TRACE(0, k, 1);
+            mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
+            tc_fence_after();
+            if (tr) QGTC_TRACE(0, k, 3);
+            unsigned mask = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxCps; ++j) {
+                if (j < CPS) {   // warp-uniform
+                    const bool nz = nojump || __any_sync(0xffffffffu, (v[j].x | v[j].y | v[j].z | v[j].w) != 0u);
+                    uint32_t r[32];
+                    if (nz) {
+                        mask |= 1u << j;
+                        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            r[ks * 8] = w[ks] & 0x01010101u;
+#pragma unroll
+                            for (int cidx = 1; cidx < 8; ++cidx)
+                                r[ks * 8 + cidx] = (use_mulhi ? __umulhi(w[ks], mult[cidx]) : (w[ks] >> cidx)) & 0x01010101u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) r[e] = 0u;
+                    }
+                    if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols + j * 32), r);
+                    else if (r[5] == 0xdeadbeefu) flags[63] = 1;  // keep the expansion alive
+                }
+            }
+            if (tr) QGTC_TRACE(0, k, 4);
+            if (!dbg_no_st) tmem_wait_st();
+            tc_fence_before();
+            if (tr) QGTC_TRACE(0, k, 5);
+            if (lane == 0) flags[s * 8 + warp] = (unsigned char)mask;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (tr) QGTC_TRACE(0, k, 6);
+            slot += 2;
+            if (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
+            s += 2;
+            if (s >= S) { s -= S; ++use; }
+        }
+    } else if (warp == kALoaderWarp) {
+        // ===================== adjacency TMA loader =====================
+        if (lane == 0 && !dbg_no_ldg) {
+            const uint32_t bytes = (uint32_t)(128 * 16 * CPS);
+            Cursor cur;
+            cur.init(0, nst, kRawSlots);
+            int l_tl = -1, row0 = 0, z = 0;
+            for (int it = 0; it < n_items; ++it) {
+                if (cur.tl != l_tl) {
+                    l_tl = cur.tl;
+                    const int tile = (int)blockIdx.x + cur.tl * (int)gridDim.x;
+                    z = tile / T.mtiles;
+                    row0 = (tile - z * T.mtiles) * 128;
+                    if (!T.a_batched) z = 0;
+                }
+                const int slot = cur.s;
+                mbar_wait(&raw_empty[slot], (cur.use & 1) ^ 1, T.error_flag, 8);
+                mbar_expect_tx(&raw_full[slot], bytes);
+                tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, cur.c * CPS * 4, row0, z, &raw_full[slot]);
+                cur.advance(1, nst, kRawSlots);
+            }
+        }
     } else if (warp == kLoaderWarp) {
         // ===================== feature-image loader =====================
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)NP * 128u;
-            for (long long it = 0; it < n_items; ++it) {
-                const int s = (int)(it % S);
-                const uint32_t use = (uint32_t)(it / S);
-                const int tl = (int)(it / gdk), c = (int)(it % gdk);
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int z = tile / T.mtiles;
-                mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
-                mbar_expect_tx(&b_full[s], bytes);
-                bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, T.bimg + (unsigned long long)z * T.bimg_gstride + (unsigned long long)c * bytes,
-                         bytes, &b_full[s]);
+            const uint32_t chunk_bytes = (uint32_t)NP * 128u;
+            Cursor cur;
+            cur.init(0, nst, S);
+            int l_tl = -1;
+            const uint8_t* img = T.bimg;
+            for (int it = 0; it < n_items; ++it) {
+                if (cur.tl != l_tl) {
+                    l_tl = cur.tl;
+                    const int tile = (int)blockIdx.x + cur.tl * (int)gridDim.x;
+                    img = T.bimg + (unsigned long long)(tile / T.mtiles) * T.bimg_gstride;
+                }
+                const int s = cur.s;
+                const int c0 = cur.c * CPS;
+                const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
+                mbar_wait(&empty[s], (cur.use & 1) ^ 1, T.error_flag, 2);
+                if (dbg_no_bulk) {
+                    mbar_arrive(&full[s]);
+                } else {
+                    mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
+                    bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
+                }
+                cur.advance(1, nst, S);
             }
         }
     } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer =====================
+        // The whole warp runs this role with warp-uniform state (so addresses and descriptors live in
+        // uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.
+        {
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t idesc = make_idesc_i8(NP);
             const uint32_t lbo = (uint32_t)(NP / 8) * 128u, sbo = 128u;
-            long long it = 0;
+            // descriptor = constant high word | (low word that only differs in the 14-bit start address)
+            const uint64_t desc0 = make_smem_desc(__shfl_sync(0xffffffffu, smem_u32(b_stages), 0), lbo, sbo);
+            const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
+            const uint32_t lo0 = (uint32_t)desc0;
+            const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
+            const uint32_t chunk_lo = ((uint32_t)NP * 128u) >> 4;
+            const uint32_t kstep_lo = (2u * lbo) >> 4;
+            int s = 0, par = 0, buf = 0, item = 0;
+            uint32_t use = 0, duse = 0;
+            // Software-pipelined: the barrier wait and mask read of item i+1 are done before the last
+            // chunk of item i is issued, so the tensor pipe still has queued work while this warp waits.
+            auto acquire = [&](int s_, uint32_t use_, int par_) -> uint32_t {
+                mbar_wait(&full[s_], use_ & 1, T.error_flag, 4);
+                tc_fence_after();
+                uint32_t m4 = *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 8 + par_ * 4);
+                m4 |= m4 >> 16;
+                m4 |= m4 >> 8;       // OR of the four expander warps' chunk masks
+                m4 = __shfl_sync(0xffffffffu, m4, 0);
+                return dbg_no_mma ? 0u : (m4 & 0xFu);
+            };
+            uint32_t m_cur = n_items > 0 ? acquire(0, 0, 0) : 0u;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int buf = tl % T.dbufs;
-                const uint32_t duse = (uint32_t)(tl / T.dbufs);
                 mbar_wait(&d_empty[buf], (duse & 1) ^ 1, T.error_flag, 3);   // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NP);
+                const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
                 uint32_t issued = 0;
-                for (int c = 0; c < gdk; ++c, ++it) {
-                    const int s = (int)(it % S);
-                    const uint32_t use = (uint32_t)(it / S);
-                    mbar_wait(&a_full[s], use & 1, T.error_flag, 4);
-                    mbar_wait(&b_full[s], use & 1, T.error_flag, 5);
-                    tc_fence_after();
-                    const int par = (int)(it & 1);
-                    const uint32_t nz = *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s * 8 + par * 4);
-                    if (nz) {
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(dcols + s * 32);
-                        const uint32_t b_addr = smem_u32(b_stages + (size_t)s * L.b_stage_bytes);
+                for (int j0 = 0; j0 < nst; ++j0, ++item) {
+                    if (lane == 0) QGTC_TRACE(1, item, 0);
+                    const int nch = (gdk - j0 * CPS < CPS) ? gdk - j0 * CPS : CPS;
+                    const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
+                    const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
+                    int s_n = s + 1;
+                    uint32_t use_n = use;
+                    if (s_n == S) { s_n = 0; ++use_n; }
+                    uint32_t m_next = 0;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            mma_i8_ts(d_tmem, a_tmem + 8 * ks, make_smem_desc(b_addr + (uint32_t)ks * 2u * lbo, lbo, sbo), idesc, issued | (uint32_t)(ks > 0));
+                    for (int j = 0; j < kMaxCps; ++j) {
+                        if (j == kMaxCps - 1) {   // before the last chunk: get the next item ready
+                            if (lane == 0) QGTC_TRACE(1, item, 1);
+                            if (item + 1 < n_items) m_next = acquire(s_n, use_n, par ^ 1);
+                            if (lane == 0) QGTC_TRACE(1, item, 2);
                         }
-                        issued = 1;
+                        if (j < nch && ((m_cur >> j) & 1u)) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                                if (elect_one()) mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, issued | (uint32_t)(ks > 0));
+                            }
+                            issued = 1;
+                        }
                     }
-                    tc_commit(&empty[s]);   // arrives when the MMAs above have finished reading A (TMEM) and B (smem)
+                    if (elect_one()) tc_commit(&empty[s]);   // arrives when the MMAs above have finished reading A (TMEM) and B (smem)
+                    if (lane == 0) QGTC_TRACE(1, item, 3);
+                    m_cur = m_next;
+                    par ^= 1;
+                    s = s_n;
+                    use = use_n;
                 }
-                d_valid[buf] = issued;
-                mbar_arrive(&d_full[buf]);  // publishes d_valid
-                tc_commit(&d_full[buf]);    // arrives when the accumulator is complete
+                if (lane == 0) {
+                    d_valid[buf] = issued;
+                    mbar_arrive(&d_full[buf]);  // publishes d_valid
+                }
+                __syncwarp();
+                if (elect_one()) tc_commit(&d_full[buf]);    // arrives when the accumulator is complete
+                if (++buf == T.dbufs) { buf = 0; ++duse; }
             }
         }
     } else {
@@ -374,8 +529,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             const uint32_t duse = (uint32_t)(tl / T.dbufs);
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int z = tile / T.mtiles, m = (tile % T.mtiles) * 128 + 32 * q + lane;
+            if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
             mbar_wait(&d_full[buf], duse & 1, T.error_flag, 6);
             tc_fence_after();
+            if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
             const bool valid = d_valid[buf] != 0;
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
             if (EPI == kEpiFloat) {
@@ -431,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);
+            if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 2);
         }
     }
 
@@ -443,13 +601,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
 }
 
 unsigned int* g_error_flag = nullptr;  // one device word per process (first device used)
+unsigned long long* g_trace = nullptr;  // clock64 trace buffer, only with QGTC_TC05_TRACE=1
+constexpr size_t kTraceWords = 3 * (size_t)kTraceItems * 8;
 
 }  // namespace
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// x1 must hold the whole R(1, M, K) plane of every problem for the TMA path (no zero-extension cases)
+static bool a_in_bounds(const GemmArgs& a) { return a.x1_words >= (unsigned long long)p8(a.M) * a.gdk * 4; }
+
 bool tc05_supports(const GemmArgs& a, int epi) {
     if (epi != kEpiBitsRow && epi != kEpiFloat) return false;
-    if (a.bit1 != 1) return false;                 // the producers expand a single adjacency plane
+    if (a.bit1 != 1) return false;                 // the expanders handle a single adjacency plane
     if (p8(a.N) > 256) return false;               // one MMA N block
+    if (!a_in_bounds(a) || !encode_tiled_fn()) return false;
     // worth it only when there is enough work to amortise the feature-image prepass
     const double ops = 2.0 * a.M * (double)a.K * a.N * a.count;
     return ops >= 2.0e9;
@@ -457,21 +634,45 @@ bool tc05_supports(const GemmArgs& a, int epi) {
 
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     if (epi != kEpiBitsRow && epi != kEpiFloat) return QGTC_ERR_UNSUPPORTED;
-    if (a.bit1 != 1 || p8(a.N) > 256) return QGTC_ERR_UNSUPPORTED;
+    if (a.bit1 != 1 || p8(a.N) > 256 || !a_in_bounds(a)) return QGTC_ERR_UNSUPPORTED;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return QGTC_ERR_UNSUPPORTED;
     Tc05Args T;
     T.g = a;
     T.NP = ((p8(a.N) + 15) / 16) * 16;
-    T.dbufs = (2 * T.NP + 4 * 32 <= kTmemCols) ? 2 : 1;
-    int stages = (kTmemCols - T.dbufs * T.NP) / 32;
+    T.cps = 256 / T.NP;
+    if (T.cps > kMaxCps) T.cps = kMaxCps;
+    if (T.cps < 1) T.cps = 1;
+    if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
+    T.nst = (a.gdk + T.cps - 1) / T.cps;
+    T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
+    int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
-    while (stages > 2 && smem_layout(T.NP, stages).total > 200 * 1024) --stages;
-    stages &= ~1;   // producers alternate by chunk parity: keep the ring even
+    while (stages > 2 && smem_layout(T.NP, stages, T.cps).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
     T.mtiles = (p8(a.M) + 127) / 128;
     T.total_tiles = T.mtiles * a.count;
     T.epi = epi;
-    T.bimg_gstride = (unsigned long long)a.gdk * T.NP * 128;
+    T.one = 1u;
+    if ((long long)((T.total_tiles + kNumSMs - 1) / kNumSMs + 1) * T.nst > (1ll << 30)) return QGTC_ERR_UNSUPPORTED;
+    const bool b_shared = a.count > 1 && a.x2_bstride == 0;   // every problem aliases one feature matrix: one image
+    T.bimg_gstride = b_shared ? 0ull : (unsigned long long)a.gdk * T.NP * 128;
+
+    // tensor map of the packed adjacency: uint32 [count][P8(M)][gdk*4], box = [1][128][4*cps]
+    alignas(64) CUtensorMap tmap;
+    {
+        T.a_batched = (a.count > 1 && a.x1_bstride != 0) ? 1 : 0;
+        const cuuint64_t row_bytes = (cuuint64_t)a.gdk * 16;
+        cuuint64_t dims[3] = {(cuuint64_t)a.gdk * 4, (cuuint64_t)p8(a.M), (cuuint64_t)(T.a_batched ? a.count : 1)};
+        cuuint64_t strides[2] = {row_bytes, T.a_batched ? (cuuint64_t)a.x1_bstride * 4 : row_bytes * (cuuint64_t)p8(a.M)};
+        cuuint32_t box[3] = {(cuuint32_t)(4 * T.cps), 128u, 1u};
+        cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUtensorMapSwizzle sw = T.cps == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : (T.cps == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t*>(a.x1), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return QGTC_ERR_UNSUPPORTED;
+    }
 
     cudaError_t e;
     if (!g_error_flag) {
@@ -480,26 +681,49 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         cudaMemset(g_error_flag, 0, sizeof(unsigned int));
     }
     T.error_flag = g_error_flag;
+    static const bool want_trace = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
+    if (want_trace && !g_trace) {
+        if (cudaMalloc(&g_trace, kTraceWords * 8) != cudaSuccess) g_trace = nullptr;
+    }
+    if (g_trace) cudaMemsetAsync(g_trace, 0, kTraceWords * 8, st);
+    T.trace = g_trace;
+    {   // keep the stream-ordered pool from handing memory back to the OS at every synchronisation
+        static thread_local int pool_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != pool_dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            cudaGetLastError();
+            pool_dev = dev;
+        }
+    }
     uint8_t* img = nullptr;
-    const size_t img_bytes = (size_t)T.bimg_gstride * a.count;
+    const int img_problems = b_shared ? 1 : a.count;
+    const size_t img_bytes = (size_t)a.gdk * T.NP * 128 * img_problems;
     e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes, st);
     if (e != cudaSuccess) return record_cuda_error(e, "cudaMallocAsync(feature image)");
     T.bimg = img;
 
-    const long long prep_items = (long long)a.gdk * T.NP * 4 * a.count;
+    GemmArgs pa = a;
+    pa.count = img_problems;
+    const long long prep_items = (long long)a.gdk * T.NP * 4 * img_problems;
     long long pgrid = (prep_items + 255) / 256;
     if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, 0, st>>>(a, img, T.bimg_gstride, T.NP);
+    prep_b_kernel<<<(int)pgrid, 256, 0, st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP);
     note_launch();
     int rc = check_launch("prep_b_kernel");
 
     if (rc == QGTC_OK) {
-        const int smem = smem_layout(T.NP, T.stages).total + 128;
+        const int smem = smem_layout(T.NP, T.stages, T.cps).total + 1024;
         const int grid = T.total_tiles < kNumSMs ? T.total_tiles : kNumSMs;
         auto launch = [&](auto kfn) -> int {
             cudaError_t e2 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaFuncSetAttribute(gemm_tc05)");
-            kfn<<<grid, kThreads, smem, st>>>(T);
+            kfn<<<grid, kThreads, smem, st>>>(T, tmap);
             note_launch();
             return check_launch("gemm_tc05_kernel");
         };
@@ -508,6 +732,15 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     e = cudaFreeAsync(img, st);
     if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "cudaFreeAsync(feature image)");
     return rc;
+}
+
+// debugging aid (not part of the public ABI): copy the last clock64 trace to the host
+extern "C" int qgtc_debug_tc05_trace(unsigned long long* dst, size_t max_words) {
+    if (!g_trace) return 0;
+    const size_t n = max_words < kTraceWords ? max_words : kTraceWords;
+    cudaDeviceSynchronize();
+    cudaMemcpy(dst, g_trace, n * 8, cudaMemcpyDeviceToHost);
+    return (int)n;
 }
 
 }  // namespace qgtc
