@@ -17,8 +17,8 @@
 //
 // A pipeline stage covers `cps` K chunks of 128 bits (cps * NP = 256, so a stage is always 16
 // column-64-equivalent MMAs) to amortise the per-stage barrier round trips.
-// Warp roles: warps 0-7 adjacency expanders (two groups alternating stages), 8-11 epilogue,
-// 12 feature loader, 13 MMA issuer, 14 adjacency TMA loader.
+// Warp roles: warps 0-15 adjacency expanders (warp = TMEM lane quarter x chunk of the stage),
+// 16-23 epilogue (lane quarter x column half), 24 feature loader, 25 MMA issuer, 26 adjacency TMA loader.
 // Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero skips the expansion and
 // reports it; if the whole 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.
 #include <cuda.h>
@@ -31,12 +31,13 @@ namespace qgtc {
 
 namespace {
 
-constexpr int kProducerWarps = 8;
-constexpr int kEpilogueWarp0 = 8;
-constexpr int kLoaderWarp = 12;
-constexpr int kMmaWarp = 13;
-constexpr int kALoaderWarp = 14;
-constexpr int kThreads = 15 * 32;
+constexpr int kProducerWarps = 16;
+constexpr int kEpilogueWarp0 = 16;
+constexpr int kEpilogueWarps = 8;
+constexpr int kLoaderWarp = 24;
+constexpr int kMmaWarp = 25;
+constexpr int kALoaderWarp = 26;
+constexpr int kThreads = 27 * 32;
 constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
 constexpr int kMaxStages = 4;
 constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
@@ -50,6 +51,8 @@ struct Tc05Args {
     int stages;                     // A (TMEM) / B (smem) ring depth
     int cps;                        // K chunks per stage (1, 2 or 4)
     int nst;                        // stages per tile = ceil(gdk / cps)
+    int wch;                        // chunks each expander warp handles per item (2 when cps == 4, else 1)
+    int wpi;                        // expander warps per item = 4 * cps / wch; the 16 warps form 16 / wpi groups
     int dbufs;                      // accumulator buffers (1 or 2)
     int mtiles;                     // 128-row tiles per problem
     int total_tiles;                // count * mtiles
@@ -209,7 +212,7 @@ __host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps) {
     L.b_stage_bytes = cps * NP * 128;
     L.bars = L.b_stage0 + stages * L.b_stage_bytes;
     L.flags = L.bars + (2 * kMaxStages + 2 * kRawSlots + 4) * 8;
-    L.misc = L.flags + kMaxStages * 8;
+    L.misc = L.flags + kMaxStages * 16;
     L.total = L.misc + 32;
     return L;
 }
@@ -283,22 +286,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     uint64_t* raw_empty = raw_full + kRawSlots;     // [kRawSlots]  4 expander warps -> adjacency loader
     uint64_t* d_full = raw_empty + kRawSlots;       // [2] MMA -> epilogue   (count 2: commit + plain arrive)
     uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 4 warps)
-    volatile unsigned char* flags = smem_raw + L.flags;  // [stage][8]: per expander warp, bit j = chunk j of the stage is non-zero
+    volatile unsigned char* flags = smem_raw + L.flags;  // [stage][chunk][lane quarter]: that expander warp's 32 x 128 bits are non-zero
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.misc);
     volatile uint32_t* d_valid = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc + 8);  // [2]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
-            mbar_init(&full[s], 5);
+            mbar_init(&full[s], T.wpi + 1);         // the expander warps of one item + the feature copy's expect_tx
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < kRawSlots; ++s) {
             mbar_init(&raw_full[s], 1);
-            mbar_init(&raw_empty[s], 4);
+            mbar_init(&raw_empty[s], T.wpi);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 2);
-            mbar_init(&d_empty[b], 4);
+            mbar_init(&d_empty[b], kEpilogueWarps);
         }
         fence_mbar_init();
     }
@@ -321,15 +324,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
 
     if (warp < kProducerWarps) {
         // ===================== adjacency expanders =====================
-        const int q = warp & 3, par = warp >> 2;   // TMEM lane quarter; this warp takes the items with it % 2 == par
+        // warp = (TMEM lane quarter q, slot t).  An item (stage) is expanded by wpi warps, each taking
+        // wch chunks; the 16 warps form G = 16 / wpi groups that take the items round-robin, so a warp
+        // has G item periods to get through its (latency-bound) wait / expand / store / signal chain.
+        const int q = warp & 3, t = warp >> 2;
+        const int WCH = T.wch, spi = T.wpi >> 2, G = kProducerWarps / T.wpi;
+        const int g = t / spi, c0 = (t - g * spi) * WCH;
         const int row = 32 * q + lane;             // row of the tile == TMEM lane
-        const int my_items = (n_items - par + 1) / 2;
-        // byte offset of logical 16-byte chunk j of this row inside a raw slot, with the TMA swizzle
+        const int my_items = (n_items - g + G - 1) / G;
+        // byte offsets of this warp's 16-byte chunks of the row inside a raw slot, with the TMA swizzle
         // (Swizzle<log2(cps),4,3>: address bits [4,4+log2 cps) ^= bits [7,7+log2 cps))
-        uint32_t off[kMaxCps];
+        uint32_t off[2];
 #pragma unroll
-        for (int j = 0; j < kMaxCps; ++j) {
-            uint32_t o = (uint32_t)(row * 16 * CPS + 16 * j);
+        for (int j = 0; j < 2; ++j) {
+            uint32_t o = (uint32_t)(row * 16 * CPS + 16 * (c0 + j));
             o ^= ((o >> 7) & (uint32_t)(CPS - 1)) << 4;
             off[j] = o;
         }
@@ -339,31 +347,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         for (int c = 1; c < 8; ++c) mult[c] = T.one << (32 - c);
         mult[0] = 0;
 
-        int slot = par, s = par;                   // raw ring slot and TMEM/B stage of the current item
-        uint32_t raw_use = 0, use = 0;
-        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)dcols;
+        int slot = g % kRawSlots, s = g % S;       // raw ring slot and TMEM/B stage of the current item
+        uint32_t raw_use = (uint32_t)(g / kRawSlots), use = (uint32_t)(g / S);
+        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + c0 * 32);
         for (int k = 0; k < my_items; ++k) {
             const bool tr = (warp == 0 && lane == 0);
             if (tr) QGTC_TRACE(0, k, 0);
-            uint4 v[kMaxCps];
             if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7);
+            uint4 v[2];
             const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes;
-#pragma unroll
-            for (int j = 0; j < kMaxCps; ++j) v[j] = (j < CPS) ? *reinterpret_cast<const uint4*>(src + off[j]) : make_uint4(0u, 0u, 0u, 0u);
+            v[0] = *reinterpret_cast<const uint4*>(src + off[0]);
+            v[1] = WCH > 1 ? *reinterpret_cast<const uint4*>(src + off[1]) : make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[slot]);       // the slot can be refilled while we expand
             if (tr) QGTC_TRACE(0, k, 1);
             mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
             tc_fence_after();
             if (tr) QGTC_TRACE(0, k, 3);
-            unsigned mask = 0;
+            unsigned nzmask = 0;
 #pragma unroll
-            for (int j = 0; j < kMaxCps; ++j) {
-                if (j < CPS) {   // warp-uniform
+            for (int j = 0; j < 2; ++j) {
+                if (j < WCH) {   // warp-uniform
                     const bool nz = nojump || __any_sync(0xffffffffu, (v[j].x | v[j].y | v[j].z | v[j].w) != 0u);
                     uint32_t r[32];
                     if (nz) {
-                        mask |= 1u << j;
+                        nzmask |= 1u << j;
                         const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
@@ -377,21 +385,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         for (int e = 0; e < 32; ++e) r[e] = 0u;
                     }
                     if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols + j * 32), r);
-                    else if (r[5] == 0xdeadbeefu) flags[63] = 1;  // keep the expansion alive
+                    else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
                 }
             }
             if (tr) QGTC_TRACE(0, k, 4);
             if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
             if (tr) QGTC_TRACE(0, k, 5);
-            if (lane == 0) flags[s * 8 + warp] = (unsigned char)mask;
+            if (lane < WCH) flags[s * 16 + (c0 + lane) * 4 + q] = (unsigned char)((nzmask >> lane) & 1u);
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (tr) QGTC_TRACE(0, k, 6);
-            slot += 2;
-            if (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
-            s += 2;
-            if (s >= S) { s -= S; ++use; }
+            slot += G;
+            while (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
+            s += G;
+            while (s >= S) { s -= S; ++use; }
         }
     } else if (warp == kALoaderWarp) {
         // ===================== adjacency TMA loader =====================
@@ -447,11 +455,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         // The whole warp runs this role with warp-uniform state (so addresses and descriptors live in
         // uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.
         {
-            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; using the
+            // literal keeps every MMA operand provably warp-uniform (uniform registers, no per-MMA R2UR).
+            if (tmem_base != 0u) {
+                if (T.error_flag) atomicExch(T.error_flag, 0x40000000u | tmem_base);
+                __trap();
+            }
+            const uint32_t tb = 0u;
             const uint32_t idesc = make_idesc_i8(NP);
             const uint32_t lbo = (uint32_t)(NP / 8) * 128u, sbo = 128u;
             // descriptor = constant high word | (low word that only differs in the 14-bit start address)
-            const uint64_t desc0 = make_smem_desc(__shfl_sync(0xffffffffu, smem_u32(b_stages), 0), lbo, sbo);
+            const uint64_t desc0 = make_smem_desc(smem_u32(b_stages), lbo, sbo);
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
             const uint32_t lo0 = (uint32_t)desc0;
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
@@ -461,14 +475,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             uint32_t use = 0, duse = 0;
             // Software-pipelined: the barrier wait and mask read of item i+1 are done before the last
             // chunk of item i is issued, so the tensor pipe still has queued work while this warp waits.
-            auto acquire = [&](int s_, uint32_t use_, int par_) -> uint32_t {
+            auto acquire = [&](int s_, uint32_t use_, int) -> uint32_t {
                 mbar_wait(&full[s_], use_ & 1, T.error_flag, 4);
                 tc_fence_after();
-                uint32_t m4 = *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 8 + par_ * 4);
-                m4 |= m4 >> 16;
-                m4 |= m4 >> 8;       // OR of the four expander warps' chunk masks
-                m4 = __shfl_sync(0xffffffffu, m4, 0);
-                return dbg_no_mma ? 0u : (m4 & 0xFu);
+                // one word per chunk: the four lane quarters' "non-zero" bytes
+                const uint32_t w = lane < 4 ? *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 16 + lane * 4) : 0u;
+                const uint32_t m4 = __ballot_sync(0xffffffffu, w != 0u) & 0xFu;
+                return dbg_no_mma ? 0u : m4;
             };
             uint32_t m_cur = n_items > 0 ? acquire(0, 0, 0) : 0u;
             for (int tl = 0; tl < my_tiles; ++tl) {
@@ -493,10 +506,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                             if (lane == 0) QGTC_TRACE(1, item, 2);
                         }
                         if (j < nch && ((m_cur >> j) & 1u)) {
+                            if (elect_one()) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                if (elect_one()) mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, issued | (uint32_t)(ks > 0));
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                                    mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, issued | (uint32_t)(ks > 0));
+                                }
                             }
                             issued = 1;
                         }
@@ -518,17 +533,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             }
         }
     } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
-        const int q = warp & 3;
+        // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
+        // a warp owns the 16-column blocks cb with (cb >> 1) % 2 == half, i.e. every other 32-column word
+        const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
         const int M = P.M, N = P.N, ob = P.out_bit;
         const unsigned keep = (1u << ob) - 1u;
         const int wpr = s128(N) * 4;
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
+        int buf = 0;
+        uint32_t duse = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
-            const int buf = tl % T.dbufs;
-            const uint32_t duse = (uint32_t)(tl / T.dbufs);
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int z = tile / T.mtiles, m = (tile % T.mtiles) * 128 + 32 * q + lane;
+            const int z = tile / T.mtiles, m = (tile - z * T.mtiles) * 128 + 32 * q + lane;
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
             mbar_wait(&d_full[buf], duse & 1, T.error_flag, 6);
             tc_fence_after();
@@ -538,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             if (EPI == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out) + (unsigned long long)z * P.out_bstride;
                 for (int cb = 0; cb < NP / 16; ++cb) {
+                    if (((cb >> 1) & 1) != half) continue;
                     int v[16];
                     tmem_ld16(d_tmem + 16 * cb, v);
                     if (m < M) {
@@ -553,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 uint32_t pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const bool row_ok = m < p8(M);
                 for (int cb = 0; cb < NP / 16; ++cb) {
+                    if (((cb >> 1) & 1) != half) continue;
                     int v[16];
                     tmem_ld16(d_tmem + 16 * cb, v);
 #pragma unroll
@@ -580,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         for (int p = 0; p < 8; ++p) pw[p] = 0;
                     }
                 }
-                if (row_ok) {   // zero pad words of the row (output buffers are not pre-zeroed)
+                if (row_ok && half == 0) {   // zero pad words of the row (output buffers are not pre-zeroed)
                     for (int w = (NP + 31) / 32; w < wpr; ++w)
                         for (int p = 0; p < ob; ++p) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = 0u;
                 }
@@ -589,6 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 2);
+            if (++buf == T.dbufs) { buf = 0; ++duse; }
         }
     }
 
@@ -645,6 +664,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     if (T.cps < 1) T.cps = 1;
     if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
     T.nst = (a.gdk + T.cps - 1) / T.cps;
+    T.wch = T.cps == 4 ? 2 : 1;
+    T.wpi = 4 * T.cps / T.wch;
     T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
     int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
