@@ -1,0 +1,210 @@
+"""Batch construction for the Cluster-GCN / batched-GIN drivers (DGL-free).
+
+Host-side mirror of the reference's ``sampler.py`` (ClusterIter, ClusterTensor) and
+``partition_utils.py``: partitions -> batches of ``batch_size`` partitions -> induced subgraph ->
+dense 0/1 adjacency -> ``QGTC.val2bit`` (sampler.py:76-106).  DGL, METIS and the datasets are not
+available offline, so graphs are synthetic: a planted-partition graph whose partitions play the role
+of METIS's output (balanced parts, mostly intra-part edges), with the reference's node counts, edge
+counts, feature widths and class counts (BASELINE.json configs; dataset.py:64 uses randn features).
+
+Only the packed tensors reach the GPU hot path; everything here is preparation outside the timed
+region, exactly as in the reference (main_qgtc.py:79 builds the ClusterIter before start_time).
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+# name -> (nodes, directed edges, feature dim, classes); BASELINE.json configs[0], [2] and SURVEY 8(d)
+SHAPES = {
+    "ppi": (56944, 818716, 50, 121),
+    "ogbn-arxiv": (169343, 1166243, 128, 40),
+    "Proteins": (43471, 162088, 29, 2),        # 0_7b_eval_QGTC_batched_GIN.py:13 row, TU-Proteins sized
+    "tiny": (3000, 24000, 32, 7),
+}
+
+
+@dataclass
+class SyntheticGraph:
+    """Edge list + features + a partition of the nodes (what sampler.py gets from DGL + METIS)."""
+    name: str
+    num_nodes: int
+    src: np.ndarray
+    dst: np.ndarray
+    feat: torch.Tensor          # [num_nodes, dim] float32, CPU
+    num_classes: int
+    parts: list                 # list of int64 arrays (node ids per partition), METIS stand-in
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.src.size)
+
+
+def make_synthetic_graph(name: str = "ppi", psize: int = 1500, seed: int = 2, p_intra: float = 0.85,
+                         num_nodes: int | None = None, num_edges: int | None = None, dim: int | None = None,
+                         num_classes: int | None = None) -> SyntheticGraph:
+    """Planted-partition graph with `psize` balanced parts; seeds follow main_qgtc.py:45-47
+    (torch 3, numpy 2, random 2)."""
+    n0, e0, d0, c0 = SHAPES.get(name, SHAPES["tiny"])
+    n, e, d, c = num_nodes or n0, num_edges or e0, dim or d0, num_classes or c0
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n).astype(np.int64)
+    bounds = np.linspace(0, n, psize + 1).astype(np.int64)
+    parts = [np.sort(perm[bounds[i]:bounds[i + 1]]) for i in range(psize)]
+    part_of = np.empty(n, dtype=np.int64)
+    for i, p in enumerate(parts):
+        part_of[p] = i
+    # intra-part edges: both ends inside the source's part; the rest are uniform
+    src = rng.integers(0, n, size=e, dtype=np.int64)
+    intra = rng.random(e) < p_intra
+    dst = rng.integers(0, n, size=e, dtype=np.int64)
+    ps = part_of[src[intra]]
+    lo, hi = bounds[ps], bounds[ps + 1]
+    dst[intra] = perm[lo + (rng.random(int(intra.sum())) * (hi - lo)).astype(np.int64)]
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(n, d, generator=g)
+    return SyntheticGraph(name, n, src, dst, feat, c, parts)
+
+
+def make_small_graph_batches(num_graphs: int = 1024, graphs_per_batch: int = 32, dim: int = 29, num_classes: int = 2,
+                             seed: int = 2) -> SyntheticGraph:
+    """Batched-GIN input (BASELINE configs[3]): many small graphs (16-64 nodes, average degree ~4); a batch
+    is a group of `graphs_per_batch` graphs, i.e. a block-diagonal adjacency.  Each small graph is one
+    'partition', so the same ClusterIter builds the batches."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(16, 65, size=num_graphs)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(offs[-1])
+    srcs, dsts, parts = [], [], []
+    for i in range(num_graphs):
+        k = int(sizes[i])
+        m = 2 * k                                   # ~4 directed edges per node after symmetrisation
+        a = rng.integers(0, k, size=m) + offs[i]
+        b = rng.integers(0, k, size=m) + offs[i]
+        srcs += [a, b]
+        dsts += [b, a]
+        parts.append(np.arange(offs[i], offs[i + 1], dtype=np.int64))
+    g = torch.Generator().manual_seed(3)
+    return SyntheticGraph("small-graphs", n, np.concatenate(srcs), np.concatenate(dsts), torch.randn(n, dim, generator=g),
+                          num_classes, parts)
+
+
+class ClusterTensor(torch.nn.Module):
+    """sampler.py:12-19: a container of the two packed buffers that moves with .cuda()/.cpu()."""
+
+    def __init__(self, bit_A: torch.Tensor, bit_X: torch.Tensor):
+        super().__init__()
+        self.register_buffer("bit_A", bit_A)
+        self.register_buffer("bit_X", bit_X)
+
+    def forward(self):
+        pass
+
+
+class ClusterIter:
+    """sampler.py:21-149.  Same constructor arguments; ``g`` is a SyntheticGraph.
+
+    For every batch: node set = `batch_size` consecutive partitions of the shuffled partition list
+    (partition_utils.py:20-24), A = dense adjacency of the induced subgraph (sampler.py:80-89),
+    bit_A = val2bit(A, 1, False, False), bit_X = val2bit(X, bit_width, True, False) (sampler.py:97-102).
+    ``param`` = (A_size_0, A_size_1, X_size_0, X_size_1).
+
+    Extensions (not in the reference): ``device`` keeps the packed batches resident on a GPU instead
+    of bouncing them through host memory, and ``batch_ids`` restricts construction to this rank's
+    shard of the batches.
+    """
+
+    def __init__(self, dn, g: SyntheticGraph, psize, batch_size, seed_nid=None, use_pp=False, regular=False,
+                 bit_width=2, run_GIN=False, device=None, batch_ids=None, keep_on_cpu=False, ops=None, par_li=None):
+        self.g = g
+        self.psize = psize
+        self.batch_size = batch_size
+        self.bit_width = bit_width
+        self.regular = regular
+        self.max = int(psize // batch_size)
+        if par_li is None:
+            self.par_li = list(g.parts)[:psize]
+            random.shuffle(self.par_li)                   # sampler.py:68 (random.seed(2) set by the driver)
+        else:
+            self.par_li = list(par_li)                    # already shuffled (multi-rank runs share one order)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.cTensor_li, self.cluster_param_li, self.batch_nodes = [], [], []
+        self.batch_ids = list(range(self.max)) if batch_ids is None else list(batch_ids)
+        if ops is None:
+            import qgtc_ppopp22_b200
+            ops = qgtc_ppopp22_b200.load_extension()
+        self.ops = ops
+
+        # group the edges by batch once (an edge belongs to a batch iff both ends are in it)
+        batch_of = np.full(g.num_nodes, -1, dtype=np.int64)
+        local_id = np.zeros(g.num_nodes, dtype=np.int64)
+        for cid in range(self.max):
+            nodes = np.concatenate(self.par_li[cid * batch_size:(cid + 1) * batch_size]).astype(np.int64)
+            batch_of[nodes] = cid
+            local_id[nodes] = np.arange(nodes.size)
+            self.batch_nodes.append(nodes)
+        eb = batch_of[g.src]
+        keep = (eb >= 0) & (eb == batch_of[g.dst])
+        order = np.argsort(eb[keep], kind="stable")
+        es, ed, ebk = g.src[keep][order], g.dst[keep][order], eb[keep][order]
+        starts = np.searchsorted(ebk, np.arange(self.max + 1))
+        self.batch_edges = {}
+
+        for cid in self.batch_ids:
+            nodes = self.batch_nodes[cid]
+            n = int(nodes.size)
+            rows = torch.from_numpy(local_id[es[starts[cid]:starts[cid + 1]]])
+            cols = torch.from_numpy(local_id[ed[starts[cid]:starts[cid + 1]]])
+            self.batch_edges[cid] = (rows, cols)
+            A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+            A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
+            X = g.feat[torch.from_numpy(nodes)].to(self.device)
+            bit_A = ops.val2bit(A, 1, False, False)
+            bit_X = ops.val2bit(X, self.bit_width, True, False)
+            if keep_on_cpu:
+                bit_A, bit_X = bit_A.cpu(), bit_X.cpu()
+            self.cTensor_li.append(ClusterTensor(bit_A, bit_X))
+            self.cluster_param_li.append((n, n, n, int(X.size(1))))
+            del A
+
+    def __len__(self):
+        return len(self.cTensor_li)
+
+    def __iter__(self):
+        self.n = 0
+        return self
+
+    def __next__(self):
+        if self.n < len(self.cTensor_li):
+            item, param = self.cTensor_li[self.n], self.cluster_param_li[self.n]
+            self.n += 1
+            return item, param
+        raise StopIteration
+
+
+def shuffled_partitions(g: SyntheticGraph, psize: int):
+    """The partition order every rank must agree on (sampler.py:68 after main_qgtc.py:47's random.seed(2))."""
+    par_li = list(g.parts)[:psize]
+    random.Random(2).shuffle(par_li)
+    return par_li
+
+
+def batch_node_counts(par_li, psize: int, batch_size: int):
+    return [int(sum(len(p) for p in par_li[c * batch_size:(c + 1) * batch_size])) for c in range(int(psize // batch_size))]
+
+
+def shard_batches(costs, world_size: int):
+    """Static assignment of batches to ranks, balanced by estimated cost (longest-processing-time first).
+    Returns a list of `world_size` lists of batch ids.  Batches are independent: no halo,
+    no exchange inside the forward."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: loads[k])
+        shards[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(s) for s in shards]

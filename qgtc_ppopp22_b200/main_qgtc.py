@@ -1,0 +1,178 @@
+#!/usr/bin/env python3
+"""Cluster-GCN / batched-GIN forward benchmark on the QGTC ops -- host-side mirror of the reference's
+``main_qgtc.py`` (same command-line flags, same op sequences main_qgtc.py:128-154, same
+"Avg. Epoch: %.3f ms" line), on DGL-free synthetic graphs of the reference's shapes.
+
+Multi-GPU: batches are independent, so they are sharded across ranks (one process per GPU,
+``torchrun --nproc-per-node N``); NCCL only reduces the timing (MAX over ranks) and, on request,
+gathers a checksum of the logits.  ``--cuda-graph`` captures a rank's whole epoch once and replays it.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import qgtc_ppopp22_b200  # noqa: E402
+from qgtc_ppopp22_b200 import cluster as C  # noqa: E402
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--dataset", type=str, default="ppi")
+    p.add_argument("--gpu", type=int, default=0, help="gpu")
+    p.add_argument("--n-epochs", type=int, default=20, help="number of training epochs")
+    p.add_argument("--batch-size", type=int, default=20, help="batch size")
+    p.add_argument("--psize", type=int, default=1500, help="number of partitions")
+    p.add_argument("--dim", type=int, default=10, help="input dimension of each dataset (default=10)")
+    p.add_argument("--n-hidden", type=int, default=16, help="number of hidden gcn units (default=16)")
+    p.add_argument("--n-classes", type=int, default=10, help="number of classes (default=10)")
+    p.add_argument("--n-layers", type=int, default=1, help="number of hidden gcn layers (default=1)")
+    p.add_argument("--bit_width", type=int, default=2, help="bitwidth for QGTC quantization (default=2)")
+    p.add_argument("--use-pp", action="store_true", help="whether to use precomputation")
+    p.add_argument("--regular", action="store_true", help="whether to use DGL")
+    p.add_argument("--run_GIN", action="store_true", help="whether to run GIN model")
+    p.add_argument("--use_QGTC", action="store_true", help="whether to use QGTC")
+    p.add_argument("--zerotile_jump", action="store_true", help="whether to profile zero-tile jumping")
+    # extensions
+    p.add_argument("--cuda-graph", action="store_true", help="capture one epoch in a CUDA graph and replay it")
+    p.add_argument("--cpu-baseline", action="store_true", help="also time the torch restatement of the DGL model on the host")
+    return p
+
+
+def gcn_forward(QGTC, bit_A, bit_X, W, n, D, bw):
+    """main_qgtc.py:146-154 (3-layer GCN; the layout mismatches of the reference chain are kept: every op is
+    defined on raw memory)."""
+    bit_W1, bit_W2, bit_W3, h1, h2, out = W
+    o = QGTC.bitMM2Bit(bit_X, bit_W1, n, D, h1, bw, bw, bw)
+    o = QGTC.bitMM2Bit(bit_A, o, n, n, h1, 1, bw, bw)
+    o = QGTC.bitMM2Bit(o, bit_W2, n, h1, h2, bw, bw, bw)
+    o = QGTC.bitMM2Bit(bit_A, o, n, n, h2, 1, bw, bw)
+    o = QGTC.bitMM2Bit(o, bit_W3, n, h2, out, bw, bw, bw)
+    return QGTC.bitMM2Int(bit_A, o, n, n, h2, 1, bw, False)
+
+
+def gin_forward(QGTC, bit_A, bit_X, W, n, D, bw):
+    """main_qgtc.py:131-138."""
+    bit_W1, bit_W2, bit_W3, h1, h2, out = W
+    o = QGTC.bitMM2Bit(bit_A, bit_X, n, n, D, 1, bw, bw)
+    o = QGTC.bitMM2Bit(o, bit_W1, n, D, h1, bw, bw, bw)
+    o = QGTC.bitMM2Bit(bit_A, o, n, n, h1, 1, bw, bw)
+    o = QGTC.bitMM2Bit(o, bit_W2, n, h1, h2, bw, bw, bw)
+    o = QGTC.bitMM2Bit(bit_A, o, n, n, h2, 1, bw, bw)
+    return QGTC.bitMM2Int(o, bit_W3, n, h2, out, bw, bw, False)
+
+
+def pack_weights(QGTC, feat_size, hidden, output, bw, device):
+    """main_qgtc.py:100-110: all-ones weights, W3 in the output-layer (C8) format."""
+    W_1 = torch.ones((feat_size, hidden), device=device)
+    W_2 = torch.ones((hidden, hidden), device=device)
+    W_3 = torch.ones((hidden, output), device=device)
+    return (QGTC.val2bit(W_1, bw, True, False), QGTC.val2bit(W_2, bw, True, False), QGTC.val2bit(W_3, bw, True, True),
+            hidden, hidden, output)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def run(args, graph=None, quiet=False):
+    torch.manual_seed(3)
+    np.random.seed(2)
+    random.seed(2)
+    rank, local, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(args.gpu)
+    device = torch.device("cuda", torch.cuda.current_device())
+    QGTC = qgtc_ppopp22_b200.load_extension()
+
+    if graph is None:
+        if args.run_GIN and args.dataset in ("small-graphs", "Proteins-batched"):
+            graph = C.make_small_graph_batches()
+            args.psize, args.batch_size = len(graph.parts), 32
+        else:
+            known = args.dataset in C.SHAPES
+            graph = C.make_synthetic_graph(args.dataset, args.psize, dim=None if known else args.dim)
+    par_li = C.shuffled_partitions(graph, args.psize)
+    counts = C.batch_node_counts(par_li, args.psize, args.batch_size)
+    shards = C.shard_batches([float(n) * n for n in counts], world)      # dominant cost ~ n^2 * hidden
+    it = C.ClusterIter(args.dataset, graph, args.psize, args.batch_size, None, use_pp=False, regular=args.regular,
+                       bit_width=args.bit_width, run_GIN=args.run_GIN, device=device, batch_ids=shards[rank], ops=QGTC, par_li=par_li)
+
+    feat_size = graph.feat.shape[1]
+    bw = args.bit_width
+    torch.cuda.synchronize()
+    start_time = time.time()                                              # main_qgtc.py:96
+    W = pack_weights(QGTC, feat_size, args.n_hidden, args.n_classes, bw, device)
+    fwd = gin_forward if args.run_GIN else gcn_forward
+    last = None
+
+    def one_epoch():
+        out = None
+        for cluster, param in it:
+            out = fwd(QGTC, cluster.bit_A, cluster.bit_X, W, param[0], param[3], bw)
+        return out
+
+    if args.zerotile_jump:
+        for cluster, param in it:
+            QGTC.bitMM2Bit_base_cnt(cluster.bit_X, W[0], param[2], param[3], W[3], bw, bw, bw)
+            QGTC.bitMM2Bit_zerojump_cnt(cluster.bit_X, W[0], param[2], param[3], W[3], bw, bw, bw)
+        return {"epoch_ms": None}
+
+    if args.cuda_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            one_epoch()                                                   # warm-up outside capture
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph_obj = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_obj):
+            last = one_epoch()
+        torch.cuda.synchronize()
+        start_time = time.time()
+        for _ in range(args.n_epochs):
+            graph_obj.replay()
+    else:
+        for _ in range(args.n_epochs):
+            last = one_epoch()
+    torch.cuda.synchronize()
+    ms = (time.time() - start_time) * 1000 / args.n_epochs
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    result = {"epoch_ms": ms, "batches": len(it), "world": world,
+              "checksum": float(last.sum().item()) if last is not None else 0.0, "nodes_per_batch": int(np.mean(counts))}
+    if args.cpu_baseline and rank == 0:
+        from qgtc_ppopp22_b200 import dgl_baseline
+        full = it if world == 1 else C.ClusterIter(args.dataset, graph, args.psize, args.batch_size, None, bit_width=bw,
+                                                   run_GIN=args.run_GIN, device=device, ops=QGTC, par_li=par_li)
+        cpu_ms, cores = dgl_baseline.cpu_epoch_ms(graph, full.batch_edges, full.batch_nodes, args.n_hidden, graph.num_classes,
+                                                  run_gin=args.run_GIN)
+        result.update({"cpu_epoch_ms": cpu_ms, "cpu_cores": cores})
+    if rank == 0 and not quiet:
+        print("Avg. Epoch: {:.3f} ms".format(ms))                         # main_qgtc.py:159, parsed by parse_time.py
+        if "cpu_epoch_ms" in result:
+            print("CPU (torch restatement of the DGL model, %d cores) Avg. Epoch: %.3f ms" % (result["cpu_cores"], result["cpu_epoch_ms"]))
+    return result
+
+
+if __name__ == "__main__":
+    a = build_parser().parse_args()
+    print(a)
+    run(a)

@@ -1,0 +1,103 @@
+"""CPU tests of the host-side driver logic: synthetic graphs, batch planning, sharding across ranks
+(world_size 2 over gloo), and the torch restatement of the DGL baseline."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from qgtc_ppopp22_b200 import cluster as C
+from qgtc_ppopp22_b200 import dgl_baseline as B
+
+
+def test_synthetic_graph_shapes_and_partitions():
+    g = C.make_synthetic_graph("ppi", 1500)
+    assert (g.num_nodes, g.num_edges, tuple(g.feat.shape), g.num_classes) == (56944, 818716, (56944, 50), 121)
+    allnodes = np.concatenate(g.parts)
+    assert allnodes.size == g.num_nodes and np.array_equal(np.sort(allnodes), np.arange(g.num_nodes))
+    sizes = [len(p) for p in g.parts]
+    assert max(sizes) - min(sizes) <= 1                                  # balanced, like METIS output
+    # 1500 partitions, 20 per batch -> 75 batches of ~759 nodes
+    counts = C.batch_node_counts(C.shuffled_partitions(g, 1500), 1500, 20)
+    assert len(counts) == 75 and 750 <= min(counts) and max(counts) <= 770
+
+
+def test_shuffle_is_rank_independent():
+    g = C.make_synthetic_graph("tiny", 60)
+    random.seed(123)
+    a = C.shuffled_partitions(g, 60)
+    random.seed(999)
+    b = C.shuffled_partitions(g, 60)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_batches_covers_and_balances(world):
+    rng = np.random.default_rng(0)
+    costs = list(rng.integers(500, 3000, size=75).astype(float) ** 2)
+    shards = C.shard_batches(costs, world)
+    assert sorted(sum(shards, [])) == list(range(75))
+    loads = [sum(costs[i] for i in s) for s in shards]
+    assert max(loads) <= 1.25 * (sum(costs) / world)
+
+
+def test_small_graph_batches():
+    g = C.make_small_graph_batches(num_graphs=64)
+    assert len(g.parts) == 64 and all(16 <= len(p) <= 64 for p in g.parts)
+    part_of = np.empty(g.num_nodes, dtype=np.int64)
+    for i, p in enumerate(g.parts):
+        part_of[p] = i
+    assert (part_of[g.src] == part_of[g.dst]).all()                       # block-diagonal
+
+
+def test_baseline_models_match_dense_math():
+    torch.manual_seed(0)
+    n, d, h, c = 40, 7, 5, 3
+    rows, cols = torch.randint(0, n, (200,)), torch.randint(0, n, (200,))
+    A = B.batch_csr(rows, cols, n)
+    dense = torch.zeros(n, n)
+    dense.index_put_((cols, rows), torch.ones(200), accumulate=True)      # out[dst] += h[src]
+    x = torch.randn(n, d)
+    sage, gin = B.GraphSAGE(d, h, c), B.GIN(d, h, c)
+    hh = x
+    for lin in sage.layers:
+        hh = torch.relu(lin(dense @ hh))
+    assert torch.allclose(sage(A, x), hh, atol=1e-4)
+    hh = x
+    for lin in gin.layers:
+        hh = lin(hh + dense @ hh)
+    assert torch.allclose(gin(A, x), hh, atol=1e-4)
+
+
+def _rank_main(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = C.make_synthetic_graph("tiny", 60)
+    par = C.shuffled_partitions(g, 60)
+    counts = C.batch_node_counts(par, 60, 4)
+    shards = C.shard_batches([float(n) * n for n in counts], world)
+    mine = torch.zeros(len(counts), dtype=torch.int64)
+    mine[shards[rank]] = 1
+    dist.all_reduce(mine)                                                 # every batch owned by exactly one rank
+    t = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                              # the epoch time is the slowest rank's
+    q.put((rank, mine.tolist(), float(t.item()), [int(c) for c in counts]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, owned, tmax, counts in res:
+        assert owned == [1] * len(counts)
+        assert tmax == 11.0

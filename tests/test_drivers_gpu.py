@@ -1,0 +1,63 @@
+"""GPU test of the drivers: ClusterIter + the main_qgtc op sequences on a small synthetic graph, every
+batch's output compared with the oracle chain on the same adjacency / features."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("run_gin", [False, True])
+@pytest.mark.parametrize("bits", [1, 2])
+def test_cluster_forward_matches_oracle(coracle, run_gin, bits):
+    import qgtc_ppopp22_b200
+    from qgtc_ppopp22_b200 import cluster as C
+    from qgtc_ppopp22_b200 import main_qgtc as drv
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    g = C.make_synthetic_graph("tiny", 60)
+    par = C.shuffled_partitions(g, 60)
+    it = C.ClusterIter("tiny", g, 60, 20, None, bit_width=bits, run_GIN=run_gin, ops=QGTC, par_li=par)
+    assert len(it) == 3
+    D, h, ncls = g.feat.shape[1], 16, 10
+    W = drv.pack_weights(QGTC, D, h, ncls, bits, torch.device("cuda"))
+    o = coracle
+    oW = (o.val2bit(np.ones((D, h), np.float32), bits, True, False), o.val2bit(np.ones((h, h), np.float32), bits, True, False),
+          o.val2bit(np.ones((h, ncls), np.float32), bits, True, True))
+    fwd = drv.gin_forward if run_gin else drv.gcn_forward
+    for cid, (cluster, param) in zip(it.batch_ids, it):
+        n = param[0]
+        got = fwd(QGTC, cluster.bit_A, cluster.bit_X, W, n, D, bits).cpu().numpy()
+        rows, cols = it.batch_edges[cid]
+        A = np.zeros((n, n), np.float32)
+        A[rows.numpy(), cols.numpy()] = 1.0
+        X = g.feat[torch.from_numpy(it.batch_nodes[cid])].numpy()
+        bA, bX = o.val2bit(A, 1, False, False), o.val2bit(X, bits, True, False)
+        assert np.array_equal(cluster.bit_A.cpu().numpy().view(np.uint32), bA)
+        b = bits
+        if run_gin:
+            t = o.bitMM2Bit(bA, bX, n, n, D, 1, b, b)
+            t = o.bitMM2Bit(t, oW[0], n, D, h, b, b, b)
+            t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+            t = o.bitMM2Bit(t, oW[1], n, h, h, b, b, b)
+            t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+            want = o.bitMM2Int(t, oW[2], n, h, ncls, b, b, False)
+        else:
+            t = o.bitMM2Bit(bX, oW[0], n, D, h, b, b, b)
+            t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+            t = o.bitMM2Bit(t, oW[1], n, h, h, b, b, b)
+            t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+            t = o.bitMM2Bit(t, oW[2], n, h, ncls, b, b, b)
+            want = o.bitMM2Int(bA, t, n, n, h, 1, b, False)
+        assert np.array_equal(got, want)
+
+
+def test_epoch_runner_eager_and_graph():
+    from qgtc_ppopp22_b200 import cluster as C
+    from qgtc_ppopp22_b200 import main_qgtc as drv
+    g = C.make_synthetic_graph("tiny", 60)
+    a = drv.build_parser().parse_args(["--dataset", "tiny", "--psize", "60", "--batch-size", "20", "--n-epochs", "2", "--use_QGTC"])
+    r1 = drv.run(a, graph=g, quiet=True)
+    a.cuda_graph = True
+    r2 = drv.run(a, graph=g, quiet=True)
+    assert r1["batches"] == 3 and r1["epoch_ms"] > 0 and r2["epoch_ms"] > 0
+    assert r1["checksum"] == r2["checksum"]
