@@ -18,7 +18,7 @@
 // A pipeline stage covers `cps` K chunks of 128 bits (cps * NP = 256, so a stage is always 16
 // column-64-equivalent MMAs) to amortise the per-stage barrier round trips.
 // Warp roles: warps 0-15 adjacency expanders (warp = TMEM lane quarter x chunk of the stage),
-// 16-23 epilogue (lane quarter x column half), 24 feature loader, 25 MMA issuer, 26 adjacency TMA loader.
+// 16-23 epilogue (lane quarter x column half), 24 feature loader, 25/27 MMA issuers, 26 adjacency TMA loader.
 // Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero skips the expansion and
 // reports it; if the whole 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.
 #include <cuda.h>
@@ -37,7 +37,8 @@ constexpr int kEpilogueWarps = 8;
 constexpr int kLoaderWarp = 24;
 constexpr int kMmaWarp = 25;
 constexpr int kALoaderWarp = 26;
-constexpr int kThreads = 27 * 32;
+constexpr int kMmaWarp2 = 27;     // second MMA issuer: takes the upper half of every stage's chunks
+constexpr int kThreads = 28 * 32;
 constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
 constexpr int kMaxStages = 4;
 constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
@@ -172,6 +173,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
@@ -284,16 +292,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     uint64_t* empty = bars + kMaxStages;            // [kMaxStages] MMA commit -> expanders, feature loader
     uint64_t* raw_full = bars + 2 * kMaxStages;     // [kRawSlots]  adjacency TMA -> expanders
     uint64_t* raw_empty = raw_full + kRawSlots;     // [kRawSlots]  4 expander warps -> adjacency loader
-    uint64_t* d_full = raw_empty + kRawSlots;       // [2] MMA -> epilogue   (count 2: commit + plain arrive)
+    uint64_t* d_full = raw_empty + kRawSlots;       // [2] MMA -> epilogue   (count 2: one commit per issuer)
     uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 4 warps)
     volatile unsigned char* flags = smem_raw + L.flags;  // [stage][chunk][lane quarter]: that expander warp's 32 x 128 bits are non-zero
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.misc);
-    volatile uint32_t* d_valid = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc + 8);  // [2]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&full[s], T.wpi + 1);         // the expander warps of one item + the feature copy's expect_tx
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], 2);                // both MMA issuers commit
         }
         for (int s = 0; s < kRawSlots; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -450,11 +457,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 cur.advance(1, nst, S);
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
-        // The whole warp runs this role with warp-uniform state (so addresses and descriptors live in
-        // uniform registers); one elected lane issues each tcgen05.mma / tcgen05.commit.
+    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+        // ===================== MMA issuers =====================
+        // Two warps issue: a tcgen05.mma of 128 x 64 x 32 keeps the tensor pipe busy ~32 cycles but one
+        // warp sustains only one issue per ~65 cycles.  Issuer 0 takes chunks [0, cps/2) of every stage,
+        // issuer 1 the rest (with cps == 1 they alternate stages).  Every MMA accumulates (the epilogue
+        // leaves the accumulator zeroed), so the order between the two issuers does not matter.
+        // Each warp runs with warp-uniform state (addresses and descriptors live in uniform registers);
+        // one elected lane issues the tcgen05 instructions.
         {
+            const int who = warp == kMmaWarp ? 0 : 1;
             // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; using the
             // literal keeps every MMA operand provably warp-uniform (uniform registers, no per-MMA R2UR).
             if (tmem_base != 0u) {
@@ -471,11 +483,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
             const uint32_t chunk_lo = ((uint32_t)NP * 128u) >> 4;
             const uint32_t kstep_lo = (2u * lbo) >> 4;
-            int s = 0, par = 0, buf = 0, item = 0;
+            // chunks [jlo, jhi) of a stage belong to this issuer
+            const int half = CPS >> 1;
+            const int jlo = CPS == 1 ? 0 : (who == 0 ? 0 : half);
+            const int jhi = CPS == 1 ? 1 : (who == 0 ? half : CPS);
+            int s = 0, buf = 0, item = 0;
             uint32_t use = 0, duse = 0;
-            // Software-pipelined: the barrier wait and mask read of item i+1 are done before the last
-            // chunk of item i is issued, so the tensor pipe still has queued work while this warp waits.
-            auto acquire = [&](int s_, uint32_t use_, int) -> uint32_t {
+            auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
                 mbar_wait(&full[s_], use_ & 1, T.error_flag, 4);
                 tc_fence_after();
                 // one word per chunk: the four lane quarters' "non-zero" bytes
@@ -483,52 +497,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 const uint32_t m4 = __ballot_sync(0xffffffffu, w != 0u) & 0xFu;
                 return dbg_no_mma ? 0u : m4;
             };
-            uint32_t m_cur = n_items > 0 ? acquire(0, 0, 0) : 0u;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                mbar_wait(&d_empty[buf], (duse & 1) ^ 1, T.error_flag, 3);   // epilogue drained this accumulator
+                mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 3);   // the epilogue has drained and zeroed this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
-                uint32_t issued = 0;
                 for (int j0 = 0; j0 < nst; ++j0, ++item) {
-                    if (lane == 0) QGTC_TRACE(1, item, 0);
+                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 0);
+                    const uint32_t m_cur = acquire(s, use);
+                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 1);
                     const int nch = (gdk - j0 * CPS < CPS) ? gdk - j0 * CPS : CPS;
                     const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
                     const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
-                    int s_n = s + 1;
-                    uint32_t use_n = use;
-                    if (s_n == S) { s_n = 0; ++use_n; }
-                    uint32_t m_next = 0;
+                    const bool mine = CPS > 1 || (item & 1) == who;
 #pragma unroll
                     for (int j = 0; j < kMaxCps; ++j) {
-                        if (j == kMaxCps - 1) {   // before the last chunk: get the next item ready
-                            if (lane == 0) QGTC_TRACE(1, item, 1);
-                            if (item + 1 < n_items) m_next = acquire(s_n, use_n, par ^ 1);
-                            if (lane == 0) QGTC_TRACE(1, item, 2);
-                        }
-                        if (j < nch && ((m_cur >> j) & 1u)) {
+                        if (mine && j >= jlo && j < jhi && j < nch && ((m_cur >> j) & 1u)) {
                             if (elect_one()) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                    mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, issued | (uint32_t)(ks > 0));
+                                    mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
                                 }
                             }
-                            issued = 1;
                         }
                     }
-                    if (elect_one()) tc_commit(&empty[s]);   // arrives when the MMAs above have finished reading A (TMEM) and B (smem)
-                    if (lane == 0) QGTC_TRACE(1, item, 3);
-                    m_cur = m_next;
-                    par ^= 1;
-                    s = s_n;
-                    use = use_n;
+                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 2);
+                    if (elect_one()) tc_commit(&empty[s]);   // arrives when this issuer's MMAs have finished reading A (TMEM) and B (smem)
+                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 3);
+                    if (++s == S) { s = 0; ++use; }
                 }
-                if (lane == 0) {
-                    d_valid[buf] = issued;
-                    mbar_arrive(&d_full[buf]);  // publishes d_valid
-                }
-                __syncwarp();
-                if (elect_one()) tc_commit(&d_full[buf]);    // arrives when the accumulator is complete
+                if (elect_one()) tc_commit(&d_full[buf]);    // arrives when this issuer's share of the accumulator is complete
                 if (++buf == T.dbufs) { buf = 0; ++duse; }
             }
         }
@@ -542,6 +540,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
         int buf = 0;
         uint32_t duse = 0;
+        // Accumulators are kept zeroed between tiles (every MMA accumulates): clear this warp's share of
+        // both buffers once, then after each read.  Column blocks follow the same ownership as the reads.
+        auto zero_my_columns = [&](int b) {
+            uint32_t z[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) z[e] = 0u;
+            for (int w32 = half; w32 * 32 < NP; w32 += 2) {
+                const uint32_t col = (uint32_t)(b * NP + w32 * 32);
+                if (w32 * 32 + 32 <= NP) tmem_st32(tmem_base + ((uint32_t)(32 * q) << 16) + col, z);
+                else tmem_st16(tmem_base + ((uint32_t)(32 * q) << 16) + col, z);   // NP % 32 == 16: a trailing half word
+            }
+            tmem_wait_st();
+        };
+        for (int b = 0; b < T.dbufs; ++b) {
+            zero_my_columns(b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[b]);
+        }
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int z = tile / T.mtiles, m = (tile - z * T.mtiles) * 128 + 32 * q + lane;
@@ -549,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             mbar_wait(&d_full[buf], duse & 1, T.error_flag, 6);
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
-            const bool valid = d_valid[buf] != 0;
+            const bool valid = true;
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
             if (EPI == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out) + (unsigned long long)z * P.out_bstride;
@@ -603,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         for (int p = 0; p < ob; ++p) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = 0u;
                 }
             }
+            zero_my_columns(buf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);

@@ -44,6 +44,7 @@ def build_parser():
     # extensions
     p.add_argument("--cuda-graph", action="store_true", help="capture one epoch in a CUDA graph and replay it")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the torch restatement of the DGL model on the host")
+    p.add_argument("--streams", type=int, default=1, help="run independent batches on this many CUDA streams (they share nothing)")
     return p
 
 
@@ -120,10 +121,26 @@ def run(args, graph=None, quiet=False):
     fwd = gin_forward if args.run_GIN else gcn_forward
     last = None
 
+    side = [torch.cuda.Stream() for _ in range(max(0, args.streams - 1))]
+
     def one_epoch():
+        """All batches of this rank once.  Batches are independent, so with --streams K they are issued
+        round-robin on K streams (forked from / joined to the current stream, which also makes the
+        pattern capturable as parallel branches of one CUDA graph)."""
         out = None
-        for cluster, param in it:
-            out = fwd(QGTC, cluster.bit_A, cluster.bit_X, W, param[0], param[3], bw)
+        if not side:
+            for cluster, param in it:
+                out = fwd(QGTC, cluster.bit_A, cluster.bit_X, W, param[0], param[3], bw)
+            return out
+        cur = torch.cuda.current_stream()
+        streams = [cur] + side
+        for st in side:
+            st.wait_stream(cur)
+        for i, (cluster, param) in enumerate(it):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                out = fwd(QGTC, cluster.bit_A, cluster.bit_X, W, param[0], param[3], bw)
+        for st in side:
+            cur.wait_stream(st)
         return out
 
     if args.zerotile_jump:

@@ -59,5 +59,7 @@ def test_epoch_runner_eager_and_graph():
     r1 = drv.run(a, graph=g, quiet=True)
     a.cuda_graph = True
     r2 = drv.run(a, graph=g, quiet=True)
-    assert r1["batches"] == 3 and r1["epoch_ms"] > 0 and r2["epoch_ms"] > 0
-    assert r1["checksum"] == r2["checksum"]
+    a.streams = 3
+    r3 = drv.run(a, graph=g, quiet=True)
+    assert r1["batches"] == 3 and r1["epoch_ms"] > 0 and r2["epoch_ms"] > 0 and r3["epoch_ms"] > 0
+    assert r1["checksum"] == r2["checksum"] == r3["checksum"]
