@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -169,13 +169,21 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    # per-launch device time of the dominant kernel (CUDA events on the launching stream)
-    evs = []
-    launches0 = capi.launch_count()
+    # clocks are sampled from here on; ~0.3 s of untimed load first so that the samples (20 ms apart)
+    # describe the loaded state the timed region runs in
     sampler = ClockSampler(local)
     barrier(world)
     if rank == 0:
         sampler.start()
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.3:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+    # per-launch device time of the dominant kernel (CUDA events on the launching stream)
+    evs = []
+    barrier(world)
+    launches0 = capi.launch_count()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -202,6 +210,14 @@ def run_ours(args):
     peaks = measured_peaks()
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
     achieved = OPS_PER_GEMM * G / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this command (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("graphs_per_launch") == G:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
 
     # ---- end to end through the host-buffer C-ABI call (pinned host operands, result read back)
     Ge = min(args.e2e_graphs, G)
@@ -234,7 +250,7 @@ def run_ours(args):
         import c_oracle
         want = c_oracle.bitMM2Bit(A[0].cpu().numpy(), X[2][0].cpu().numpy(), M, K, N, 1, 2, 2).reshape(-1)
         ok = bool(np.array_equal(outs[2][0].cpu().numpy().view(np.uint32), want))
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_port(A[0].cpu().numpy(), {b: X[b][0].cpu().numpy() for b in BITS})
 
     epoch = None
@@ -261,7 +277,7 @@ def run_ours(args):
                     "api": "qgtc_bitmm2bit_host (pinned host operands -> packed result on host)", "graphs_per_step": Ge * len(BITS)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
-                         "frac": round(achieved / int8_peak, 4), "traffic": None,
+                         "frac": round(achieved / int8_peak, 4), "traffic": traffic,
                          "note": "integer ops/s of the batched bit-GEMM kernel (mean over the four bit widths); peak = 2 x %s dense "
                                  "bf16 (sustained) from MEASURED_PEAKS.json, INT8:bf16 = 2:1 on B200" % peaks["source"]},
             "cpu_baseline": cpu,

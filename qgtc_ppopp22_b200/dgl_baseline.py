@@ -38,14 +38,19 @@ class GIN(nn.Module):
 
 def batch_csr(rows: torch.Tensor, cols: torch.Tensor, n: int) -> torch.Tensor:
     """in-edge aggregation matrix: out[dst] += h[src]  (update_all(copy_src, sum))"""
+    import warnings
     idx = torch.stack([cols, rows])            # row = destination, column = source
-    a = torch.sparse_coo_tensor(idx, torch.ones(rows.numel()), (n, n)).coalesce()
-    return a.to_sparse_csr()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = torch.sparse_coo_tensor(idx, torch.ones(rows.numel()), (n, n)).coalesce()
+        return a.to_sparse_csr()
 
 
 def cpu_epoch_ms(graph, batch_edges: dict, batch_nodes: list, n_hidden: int, n_classes: int, run_gin: bool = False,
                  epochs: int = 3, warmup: int = 1) -> tuple[float, int]:
     """Average epoch time (ms) of the baseline forward over the given batches on the host cores."""
+    import os
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the baseline gets every core
     torch.manual_seed(3)
     in_feats = graph.feat.shape[1]
     model = GIN(in_feats, n_hidden, n_classes) if run_gin else GraphSAGE(in_feats, n_hidden, n_classes)
