@@ -106,6 +106,22 @@ int qgtc_bitmm2int(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev
 int qgtc_tile_counts(const int32_t* x1_dev, size_t x1_words, int M, int K, int N, int bit1, int bit2,
                      uint64_t* total_host, uint64_t* nonzero_host, void* stream);
 
+/* Precomputed tile bitmap of a 1-bit adjacency (zero-tile jumping, reference kernel.h:574-591 lifted to the
+ * tile the tensor core consumes): bit c of word w of tile (problem z, row tile mt) is set iff rows
+ * 128mt..128mt+127 x K bits 128(32w+c)..+127 contain a one.  Words: count * ceil(P8(M)/128) * ceil(S128(K)/32)
+ * (qgtc_tile_bitmap_words).  Compute it once per adjacency (e.g. when the batch is packed) and pass it to
+ * qgtc_bitmm2bit_tilemap / qgtc_bitmm2int_tilemap: all-zero tiles are then neither loaded, expanded nor
+ * multiplied.  Results are identical to the calls without a bitmap. */
+size_t qgtc_tile_bitmap_words(int M, int K, int count);
+int qgtc_tile_bitmap(const int32_t* x1_dev, size_t x1_words, size_t x1_stride_words, int M, int K, int count,
+                     uint32_t* bitmap_dev, size_t bitmap_words, void* stream);
+int qgtc_bitmm2bit_tilemap(const int32_t* x1_dev, size_t x1_stride_words, const int32_t* x2_dev, size_t x2_stride_words,
+                           const uint32_t* bitmap_dev, int count, int M, int K, int N, int bit2, int out_bit,
+                           int32_t* out_dev, size_t out_stride_words, int engine, unsigned flags, void* stream);
+int qgtc_bitmm2int_tilemap(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev, size_t x2_words,
+                           const uint32_t* bitmap_dev, int M, int K, int N, int bit2, int pad128,
+                           float* out_dev, size_t out_elems, int engine, unsigned flags, void* stream);
+
 /* Batched bit-GEMM: `count` independent problems of identical shape, one launch (persistent CTAs).
  * Problem i uses x1 + i*x1_stride_words, x2 + i*x2_stride_words, out + i*out_stride_words.
  * This is the throughput form of bitMM2Bit_profile (QGTC_device.cu:379-434: 200 back-to-back

@@ -308,6 +308,22 @@ def tile_counts(x1, M: int, K: int, N: int, bit1: int, bit2: int) -> tuple[int, 
     return total, 32 * S8(N) * bit2 * nz
 
 
+def tile_bitmap(x1, M: int, K: int) -> np.ndarray:
+    """Checker for qgtc_tile_bitmap (this repo's extension of the zero-tile test, kernel.h:574-591, to the
+    128-row x 128-bit tile the tensor core consumes): uint32 [ceil(P8(M)/128)][ceil(S128(K)/32)], bit c of word w
+    set iff rows 128mt..128mt+127 x chunk 32w+c of plane 0 contain a one."""
+    f1 = np.asarray(x1).reshape(-1).view(np.uint32)
+    gdk = S128(K)
+    mt, bmw = (P8(M) + 127) // 128, (gdk + 31) // 32
+    idx = np.arange(P8(M))[:, None] * gdk * 4 + np.arange(gdk * 4)[None, :]
+    w = _gather_zero_ext(f1, idx).reshape(P8(M), gdk, 4)
+    nzr = (w != 0).any(axis=2)                                   # [rows, chunks]
+    pad = np.zeros((mt * 128, bmw * 32), dtype=bool)
+    pad[:P8(M), :gdk] = nzr
+    tiles = pad.reshape(mt, 128, bmw, 32).any(axis=1)            # [mt, bmw, 32]
+    return (tiles.astype(np.uint64) << np.arange(32, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint32)
+
+
 # --------------------------------------------------------------------------------------
 # value-level identity (property used by tests; not a reference function)
 # --------------------------------------------------------------------------------------

@@ -24,11 +24,21 @@ def bench(H, W, bits, col_major, copies, reps=5):
     for x in xs[:2]:
         out = capi.val2bit(x, bits, col_major, False)
     torch.cuda.synchronize()
+    # one CUDA graph over all copies: the python/ctypes call overhead (~15 us) must not starve the GPU
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for x in xs:
+                out = capi.val2bit(x, bits, col_major, False)
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for x in xs:
-            out = capi.val2bit(x, bits, col_major, False)
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (reps * copies)

@@ -48,6 +48,10 @@ if __name__ == "__main__":
             total, nz = capi.tile_counts(A[0].view(-1, M // 32 if M % 128 == 0 else -1), M, M, N, 1, b)
             out = torch.empty((G, capi.packed_words(0, b, M, N)), dtype=torch.int32, device="cuda")
             res = {"M": M, "N": N, "bits": b, "pattern": kind, "density": p, "graphs": G, "nonzero_tile_ratio": round(nz / total, 4)}
+            bm = capi.tile_bitmap(A, M, M, G)
+            ms = timed(lambda: capi.bitMM2Bit_tilemap(A, X, bm, G, M, M, N, b, b, out=out, engine=capi.ENGINE_TCGEN05))
+            res["tcgen05_tilemap_tops"] = round(2.0 * M * M * N * G / (ms * 1e-3) / 1e12, 1)
+            res["tile128_nonzero_ratio"] = round(float(sum(bin(int(v) & 0xffffffff).count("1") for v in bm.cpu().numpy().reshape(-1).tolist())) / (G * ((M + 127) // 128) ** 2), 4)
             for eng_name, eng in (("tcgen05", capi.ENGINE_TCGEN05), ("mma", capi.ENGINE_MMA_SYNC)):
                 for jname, fl in (("jump", 0), ("nojump", capi.FLAG_NO_ZERO_JUMP)):
                     ms = timed(lambda: capi.bitMM2Bit_batched(A, X, G, M, M, N, 1, b, b, out=out, engine=eng, flags=fl))

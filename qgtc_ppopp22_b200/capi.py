@@ -23,6 +23,7 @@ SYMBOLS = [
     "qgtc_abi_version", "qgtc_strerror", "qgtc_last_cuda_error", "qgtc_packed_words", "qgtc_packed_shape",
     "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
+    "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
 ]
 
 _LIB = None
@@ -62,6 +63,11 @@ def lib() -> ctypes.CDLL:
         L.qgtc_bitmm2bit_batched.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2bit_host.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_launch_count.restype = c.c_uint64
+        L.qgtc_tile_bitmap_words.restype = sz
+        L.qgtc_tile_bitmap_words.argtypes = [i, i, i]
+        L.qgtc_tile_bitmap.argtypes = [vp, sz, sz, i, i, i, vp, sz, vp]
+        L.qgtc_bitmm2bit_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm2int_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         _LIB = L
     return _LIB
 
@@ -176,6 +182,42 @@ def bitMM2Bit_batched(x1, x2, count, M, K, N, bit1, bit2, out_bit, out=None, eng
             out = torch.empty((count, wo), dtype=torch.int32, device=x1.device)
         _check(lib().qgtc_bitmm2bit_batched(x1.data_ptr(), s1, x2.data_ptr(), s2, count, M, K, N, bit1, bit2, out_bit,
                                             out.data_ptr(), wo if out.numel() >= count * wo else 0, engine, flags, _stream()), "bitMM2Bit_batched")
+    return out
+
+
+def tile_bitmap(x1: torch.Tensor, M: int, K: int, count: int = 1) -> torch.Tensor:
+    """Tile bitmap of `count` packed 1-bit adjacencies (x1: [count, words] or one problem's words)."""
+    _req_cuda(x1, torch.int32, "bit_X1")
+    w1 = packed_words(LAYOUT_ROW, 1, M, K)
+    stride = 0 if count == 1 else w1
+    words = int(lib().qgtc_tile_bitmap_words(M, K, count))
+    with torch.cuda.device(x1.device):
+        bm = torch.empty((count, words // count), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_tile_bitmap(x1.data_ptr(), x1.numel() if count == 1 else w1, stride, M, K, count, bm.data_ptr(), words, _stream()), "tile_bitmap")
+    return bm
+
+
+def bitMM2Bit_tilemap(x1, x2, tile_map, count, M, K, N, bit2, out_bit, out=None, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """bitMM2Bit (1-bit X1) for `count` problems with a precomputed tile bitmap: zero tiles are not loaded."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2"); _req_cuda(tile_map, torch.int32, "tile_map")
+    w1, w2, wo = packed_words(LAYOUT_ROW, 1, M, K), packed_words(LAYOUT_COL128, bit2, K, N), packed_words(LAYOUT_ROW, out_bit, M, N)
+    if x1.numel() != count * w1 or x2.numel() not in (w2, count * w2):
+        raise QgtcError("tilemap operands must hold `count` well-formed problems")
+    s2 = 0 if (count > 1 and x2.numel() == w2) else w2
+    with torch.cuda.device(x1.device):
+        if out is None:
+            out = torch.empty((count, wo), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_bitmm2bit_tilemap(x1.data_ptr(), w1, x2.data_ptr(), s2, tile_map.data_ptr(), count, M, K, N, bit2, out_bit,
+                                            out.data_ptr(), wo, engine, flags, _stream()), "bitMM2Bit_tilemap")
+    return out
+
+
+def bitMM2Int_tilemap(x1, x2, tile_map, M, K, N, bit2, pad_128=False, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2"); _req_cuda(tile_map, torch.int32, "tile_map")
+    with torch.cuda.device(x1.device):
+        out = torch.empty((M, N), dtype=torch.float32, device=x1.device)
+        _check(lib().qgtc_bitmm2int_tilemap(x1.data_ptr(), x1.numel(), x2.data_ptr(), x2.numel(), tile_map.data_ptr(), M, K, N, bit2,
+                                            int(bool(pad_128)), out.data_ptr(), out.numel(), engine, flags, _stream()), "bitMM2Int_tilemap")
     return out
 
 

@@ -14,6 +14,7 @@ namespace qgtc {
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st);
 int launch_bit2val(const uint32_t* in, size_t in_words, int nbits, int H, int W, int col_major, int* out, cudaStream_t st);
 int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K, int bit1, unsigned long long* nz_dev, cudaStream_t st);
+int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int M, int K, int count, uint32_t* bitmap, cudaStream_t st);
 int launch_gemm_mma(const GemmArgs& a, int epi, cudaStream_t st);
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st);   // QGTC_ERR_UNSUPPORTED when the shape does not qualify
 bool tc05_supports(const GemmArgs& a, int epi);
@@ -221,6 +222,51 @@ int qgtc_bitmm2bit_batched(const int32_t* x1_dev, size_t x1_stride_words, const 
     a.out_bstride = out_stride_words;
     if (int rc = check_device()) return rc;
     return run_gemm(a, kEpiBitsRow, engine, (cudaStream_t)stream);
+}
+
+size_t qgtc_tile_bitmap_words(int M, int K, int count) {
+    if (M <= 0 || K <= 0 || count <= 0) return 0;
+    return (size_t)count * ((p8(M) + 127) / 128) * ((s128(K) + 31) / 32);
+}
+
+int qgtc_tile_bitmap(const int32_t* x1_dev, size_t x1_words, size_t x1_stride_words, int M, int K, int count,
+                     uint32_t* bitmap_dev, size_t bitmap_words, void* stream) {
+    if (!x1_dev || !bitmap_dev || M <= 0 || K <= 0 || count <= 0) return QGTC_ERR_INVALID_ARG;
+    if (!aligned16(x1_dev) || (x1_stride_words & 3)) return QGTC_ERR_ALIGNMENT;
+    if (bitmap_words < qgtc_tile_bitmap_words(M, K, count)) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    return launch_tile_bitmap(reinterpret_cast<const uint32_t*>(x1_dev), x1_words, x1_stride_words, M, K, count, bitmap_dev, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2bit_tilemap(const int32_t* x1_dev, size_t x1_stride_words, const int32_t* x2_dev, size_t x2_stride_words,
+                           const uint32_t* bitmap_dev, int count, int M, int K, int N, int bit2, int out_bit,
+                           int32_t* out_dev, size_t out_stride_words, int engine, unsigned flags, void* stream) {
+    if (count <= 0 || count > 65535) return QGTC_ERR_INVALID_ARG;
+    GemmArgs a;
+    const size_t need1 = qgtc_packed_words(QGTC_LAYOUT_ROW, 1, M, K);
+    const size_t need2 = qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N);
+    const size_t need_o = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
+    if (int rc = fill_gemm_args(a, x1_dev, need1, x2_dev, need2, M, K, N, 1, bit2, out_bit, true, out_dev, flags)) return rc;
+    if ((x1_stride_words & 3) || (x2_stride_words & 3) || (out_stride_words & 3)) return QGTC_ERR_ALIGNMENT;
+    if (count > 1 && out_stride_words && out_stride_words < need_o) return QGTC_ERR_SIZE;
+    a.count = count;
+    a.x1_bstride = x1_stride_words;
+    a.x2_bstride = x2_stride_words;
+    a.out_bstride = out_stride_words;
+    a.tile_bitmap = bitmap_dev;
+    if (int rc = check_device()) return rc;
+    return run_gemm(a, kEpiBitsRow, engine, (cudaStream_t)stream);
+}
+
+int qgtc_bitmm2int_tilemap(const int32_t* x1_dev, size_t x1_words, const int32_t* x2_dev, size_t x2_words,
+                           const uint32_t* bitmap_dev, int M, int K, int N, int bit2, int pad128,
+                           float* out_dev, size_t out_elems, int engine, unsigned flags, void* stream) {
+    GemmArgs a;
+    if (int rc = fill_gemm_args(a, x1_dev, x1_words, x2_dev, x2_words, M, K, N, 1, bit2, 1, pad128 != 0, out_dev, flags)) return rc;
+    if (out_elems < (size_t)M * N) return QGTC_ERR_SIZE;
+    a.tile_bitmap = bitmap_dev;
+    if (int rc = check_device()) return rc;
+    return run_gemm(a, kEpiFloat, engine, (cudaStream_t)stream);
 }
 
 int qgtc_tile_counts(const int32_t* x1_dev, size_t x1_words, int M, int K, int N, int bit1, int bit2,

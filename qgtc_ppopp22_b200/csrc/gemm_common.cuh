@@ -25,6 +25,7 @@ struct GemmArgs {
     int gdk;   // S128(K): number of 128-bit K chunks
     int count; // batch size
     unsigned flags;
+    const uint32_t* tile_bitmap;  // optional (qgtc_tile_bitmap): [count][ceil(P8(M)/128)][ceil(S128(K)/32)] words, or null
 };
 
 // Gather bit p of four consecutive byte values (lowest address = first column) into a nibble

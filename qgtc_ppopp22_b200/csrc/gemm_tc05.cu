@@ -59,6 +59,8 @@ struct Tc05Args {
     int total_tiles;                // count * mtiles
     int epi;
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
+    const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
+    int bmw;                        // bitmap words per tile = ceil(gdk / 32)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
     unsigned int* error_flag;       // device word set by the watchdog
     unsigned long long* trace;      // optional clock64 trace of CTA 0 (QGTC_TC05_TRACE=1), else null
@@ -242,6 +244,20 @@ struct Cursor {
     }
 };
 
+// Zero-tile jumping from the precomputed bitmap: a stage (cps chunks) is visited iff one of its chunk bits is set.
+// stage_bits() collapses a word of chunk bits to one bit per stage (at the stage's first chunk position).
+__device__ __forceinline__ uint32_t stage_bits(uint32_t w, int cps) {
+    if (cps == 2) return (w | (w >> 1)) & 0x55555555u;
+    if (cps == 4) return (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+    return w;
+}
+// word w of a tile's chunk bits; without a bitmap every existing chunk counts
+__device__ __forceinline__ uint32_t tile_word(const uint32_t* bm_tile, int w, int gdk) {
+    const int left = gdk - 32 * w;
+    const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+    return bm_tile ? (__ldg(bm_tile + w) & valid) : valid;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Feature image: X2 (packed planes, raw words, zero-extension) -> u8 values in the MMA's K order,
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
@@ -314,6 +330,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     }
     if (warp == kALoaderWarp && lane == 0) prefetch_tmap(&tmapA);
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    // number of pipeline items of this CTA = non-zero stages of its tiles (all stages without a bitmap)
+    int* item_count = reinterpret_cast<int*>(smem_raw + L.misc + 16);
+    if (threadIdx.x == 0) *item_count = 0;
+    __syncthreads();
+    {
+        const int tiles_here = (T.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        int cnt = 0;
+        for (int i = threadIdx.x; i < tiles_here * T.bmw; i += blockDim.x) {
+            const int tl = i / T.bmw, w = i - tl * T.bmw;
+            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+            const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+            cnt += __popc(stage_bits(tile_word(bm_tile, w, P.gdk), T.cps));
+        }
+        if (cnt) atomicAdd(item_count, cnt);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -322,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     const int stage_cols = CPS * 32;
 
     const int my_tiles = (T.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_items = my_tiles * nst;   // launch_gemm_tc05 guarantees this fits 31 bits
+    const int n_items = *item_count;      // launch_gemm_tc05 guarantees this fits 31 bits
     const bool nojump = (P.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
     const bool dbg_no_st = (P.flags & 0x10000u) != 0, dbg_no_mma = (P.flags & 0x20000u) != 0;
@@ -412,49 +443,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         // ===================== adjacency TMA loader =====================
         if (lane == 0 && !dbg_no_ldg) {
             const uint32_t bytes = (uint32_t)(128 * 16 * CPS);
-            Cursor cur;
-            cur.init(0, nst, kRawSlots);
-            int l_tl = -1, row0 = 0, z = 0;
-            for (int it = 0; it < n_items; ++it) {
-                if (cur.tl != l_tl) {
-                    l_tl = cur.tl;
-                    const int tile = (int)blockIdx.x + cur.tl * (int)gridDim.x;
-                    z = tile / T.mtiles;
-                    row0 = (tile - z * T.mtiles) * 128;
-                    if (!T.a_batched) z = 0;
+            int slot = 0;
+            uint32_t use = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+                int z = tile / T.mtiles;
+                const int row0 = (tile - z * T.mtiles) * 128;
+                if (!T.a_batched) z = 0;
+                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                for (int w = 0; w < T.bmw; ++w) {
+                    uint32_t m = stage_bits(tile_word(bm_tile, w, gdk), CPS);
+                    while (m) {
+                        const int c0 = 32 * w + __ffs(m) - 1;   // first chunk of a non-zero stage
+                        m &= m - 1;
+                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8);
+                        mbar_expect_tx(&raw_full[slot], bytes);
+                        tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
+                        if (++slot == kRawSlots) { slot = 0; ++use; }
+                    }
                 }
-                const int slot = cur.s;
-                mbar_wait(&raw_empty[slot], (cur.use & 1) ^ 1, T.error_flag, 8);
-                mbar_expect_tx(&raw_full[slot], bytes);
-                tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, cur.c * CPS * 4, row0, z, &raw_full[slot]);
-                cur.advance(1, nst, kRawSlots);
             }
         }
     } else if (warp == kLoaderWarp) {
         // ===================== feature-image loader =====================
         if (lane == 0) {
             const uint32_t chunk_bytes = (uint32_t)NP * 128u;
-            Cursor cur;
-            cur.init(0, nst, S);
-            int l_tl = -1;
-            const uint8_t* img = T.bimg;
-            for (int it = 0; it < n_items; ++it) {
-                if (cur.tl != l_tl) {
-                    l_tl = cur.tl;
-                    const int tile = (int)blockIdx.x + cur.tl * (int)gridDim.x;
-                    img = T.bimg + (unsigned long long)(tile / T.mtiles) * T.bimg_gstride;
+            int s = 0;
+            uint32_t use = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+                const uint8_t* img = T.bimg + (unsigned long long)(tile / T.mtiles) * T.bimg_gstride;
+                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                for (int w = 0; w < T.bmw; ++w) {
+                    uint32_t m = stage_bits(tile_word(bm_tile, w, gdk), CPS);
+                    while (m) {
+                        const int c0 = 32 * w + __ffs(m) - 1;
+                        m &= m - 1;
+                        const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
+                        mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
+                        if (dbg_no_bulk) {
+                            mbar_arrive(&full[s]);
+                        } else {
+                            mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
+                            bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
+                        }
+                        if (++s == S) { s = 0; ++use; }
+                    }
                 }
-                const int s = cur.s;
-                const int c0 = cur.c * CPS;
-                const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
-                mbar_wait(&empty[s], (cur.use & 1) ^ 1, T.error_flag, 2);
-                if (dbg_no_bulk) {
-                    mbar_arrive(&full[s]);
-                } else {
-                    mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
-                    bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
-                }
-                cur.advance(1, nst, S);
             }
         }
     } else if (warp == kMmaWarp || warp == kMmaWarp2) {
@@ -501,11 +536,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 3);   // the epilogue has drained and zeroed this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
-                for (int j0 = 0; j0 < nst; ++j0, ++item) {
+                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                for (int bw = 0; bw < T.bmw; ++bw) {
+                  uint32_t sm = stage_bits(tile_word(bm_tile, bw, gdk), CPS);
+                  for (; sm; sm &= sm - 1, ++item) {
+                    const int c_first = 32 * bw + __ffs(sm) - 1;       // first chunk of this non-zero stage
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 0);
                     const uint32_t m_cur = acquire(s, use);
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 1);
-                    const int nch = (gdk - j0 * CPS < CPS) ? gdk - j0 * CPS : CPS;
+                    const int nch = (gdk - c_first < CPS) ? gdk - c_first : CPS;
                     const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
                     const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
                     const bool mine = CPS > 1 || (item & 1) == who;
@@ -525,6 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     if (elect_one()) tc_commit(&empty[s]);   // arrives when this issuer's MMAs have finished reading A (TMEM) and B (smem)
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 3);
                     if (++s == S) { s = 0; ++use; }
+                  }
                 }
                 if (elect_one()) tc_commit(&d_full[buf]);    // arrives when this issuer's share of the accumulator is complete
                 if (++buf == T.dbufs) { buf = 0; ++duse; }
@@ -694,6 +735,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.total_tiles = T.mtiles * a.count;
     T.epi = epi;
     T.one = 1u;
+    T.bitmap = a.tile_bitmap;
+    T.bmw = (a.gdk + 31) / 32;
     if ((long long)((T.total_tiles + kNumSMs - 1) / kNumSMs + 1) * T.nst > (1ll << 30)) return QGTC_ERR_UNSUPPORTED;
     const bool b_shared = a.count > 1 && a.x2_bstride == 0;   // every problem aliases one feature matrix: one image
     T.bimg_gstride = b_shared ? 0ull : (unsigned long long)a.gdk * T.NP * 128;

@@ -15,29 +15,37 @@ namespace qgtc {
 // ------------------------------------------------------------------------------------------
 constexpr int kPackUnroll = 4;
 
+// Work decomposition without divisions in the loop: `splits` warps share a row (each takes a contiguous
+// range of 128-column groups), rows are strided over the remaining warps.
 template <bool kVec>
-__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, int nbits,
+__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, int nbits, int splits,
                                                         uint32_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int gdy = s128(W);
     const int rows = p8(H);
-    const long long units = (long long)rows * gdy;
     const size_t wpr = (size_t)gdy * 4, plane = (size_t)rows * wpr;
     const float ub = (float)(1 << nbits);
     const unsigned keep = (1u << nbits) - 1u;
-    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned part = warp_id % (unsigned)splits, row0 = warp_id / (unsigned)splits, row_step = nwarps / (unsigned)splits;
+    if (row_step == 0 || row0 >= row_step) return;   // leftover warps when nwarps is not a multiple of splits
+    const int per = (gdy + splits - 1) / splits;
+    const int cg_begin = (int)part * per, cg_end = min(gdy, cg_begin + per);
+    const int p_of_lane = lane & 7, w_of_lane = lane >> 3;
 
-    for (long long u0 = warp_id * kPackUnroll; u0 < units; u0 += nwarps * kPackUnroll) {
-        float4 v[kPackUnroll];
+    for (unsigned r = row0; r < (unsigned)rows; r += row_step) {
+        const bool row_ok = r < (unsigned)H;
+        const float* xrow = x + (size_t)r * W;
+        uint32_t* orow = out + (size_t)r * wpr;
+        for (int cg0 = cg_begin; cg0 < cg_end; cg0 += kPackUnroll) {
+            float4 v[kPackUnroll];
 #pragma unroll
-        for (int j = 0; j < kPackUnroll; ++j) {
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const long long u = u0 + j;
-            if (u < units) {
-                const int r = (int)(u / gdy), c = (int)(u % gdy) * 128 + 4 * lane;
-                if (r < H && c < W) {
-                    const float* src = x + (size_t)r * W + c;
+            for (int j = 0; j < kPackUnroll; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c = (cg0 + j) * 128 + 4 * lane;
+                if (row_ok && cg0 + j < cg_end && c < W) {
+                    const float* src = xrow + c;
                     if (kVec) {
                         v[j] = __ldcs(reinterpret_cast<const float4*>(src));  // streamed once
                     } else {
@@ -48,74 +56,71 @@ __global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < kPackUnroll; ++j) {
-            const long long u = u0 + j;
-            if (u >= units) break;  // warp-uniform
-            const int r = (int)(u / gdy), cg = (int)(u % gdy);
-            const unsigned q0 = (unsigned)quantize_val(v[j].x, ub) & keep;
-            const unsigned q1 = (unsigned)quantize_val(v[j].y, ub) & keep;
-            const unsigned q2 = (unsigned)quantize_val(v[j].z, ub) & keep;
-            const unsigned q3 = (unsigned)quantize_val(v[j].w, ub) & keep;
-            const unsigned t = (q0 << 24) | (q1 << 16) | (q2 << 8) | q3;
-            unsigned mine = 0;
-            for (int p = 0; p < nbits; ++p) {
-                // bit p of the four values -> nibble, first column in the nibble's MSB
-                const unsigned nib = (((t >> p) & 0x01010101u) * 0x01020408u) >> 24;
-                unsigned w = nib << (28 - 4 * (lane & 7));
-                w |= __shfl_xor_sync(0xffffffffu, w, 1);
-                w |= __shfl_xor_sync(0xffffffffu, w, 2);
-                w |= __shfl_xor_sync(0xffffffffu, w, 4);
-                if ((lane & 7) == p) mine = w;
+            for (int j = 0; j < kPackUnroll; ++j) {
+                if (cg0 + j >= cg_end) break;  // warp-uniform
+                const unsigned q0 = (unsigned)quantize_val(v[j].x, ub) & keep;
+                const unsigned q1 = (unsigned)quantize_val(v[j].y, ub) & keep;
+                const unsigned q2 = (unsigned)quantize_val(v[j].z, ub) & keep;
+                const unsigned q3 = (unsigned)quantize_val(v[j].w, ub) & keep;
+                const unsigned t = (q0 << 24) | (q1 << 16) | (q2 << 8) | q3;
+                unsigned mine = 0;
+                for (int p = 0; p < nbits; ++p) {
+                    // bit p of the four values -> nibble, first column in the nibble's MSB
+                    const unsigned nib = (((t >> p) & 0x01010101u) * 0x01020408u) >> 24;
+                    unsigned w = nib << (28 - 4 * p_of_lane);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                    if (p_of_lane == p) mine = w;
+                }
+                if (p_of_lane < nbits) orow[(size_t)p_of_lane * plane + (size_t)(cg0 + j) * 4 + w_of_lane] = mine;
             }
-            if ((lane & 7) < nbits)
-                out[(size_t)(lane & 7) * plane + (size_t)r * wpr + (size_t)cg * 4 + (lane >> 3)] = mine;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // COL layouts: word [p][c][kw] holds rows 32kw..32kw+31 of column c, MSB-first (a transposing
-// pack).  One warp handles a 128-row x 32-column tile: every row read is a coalesced 128-byte
-// request, each lane accumulates the four words of its own column and stores them as one uint4.
+// pack).  One warp handles a 32-row x 32-column tile: every row read is a coalesced 128-byte
+// request (all 32 in flight), each lane accumulates the word of its own column per plane.
 // ------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(256) pack_col_kernel(const float* __restrict__ x, int H, int W, int col_limit,
                                                         uint32_t* __restrict__ out, unsigned long long out_words) {
     const int lane = threadIdx.x & 31;
     const int gdk = s128(H);
+    const int kwords = gdk * 4;                       // words per column
     const int cgroups = (col_limit + 31) >> 5;
-    const long long units = (long long)gdk * cgroups;
-    const size_t plane = (size_t)gdk * p128(W) * 4;  // reference kernel.h:88: always the P128 stride
+    const unsigned units = (unsigned)kwords * (unsigned)cgroups;
+    const size_t plane = (size_t)gdk * p128(W) * 4;   // reference kernel.h:88: always the P128 stride
     const float ub = (float)(1 << NB);
     const unsigned keep = (1u << NB) - 1u;
-    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
 
-    for (long long u = warp_id; u < units; u += nwarps) {
-        const int kb = (int)(u % gdk), c = (int)(u / gdk) * 32 + lane;
-        uint32_t w[NB][4];
+    for (unsigned u = warp_id; u < units; u += nwarps) {
+        const int kw = (int)(u % (unsigned)kwords), c = (int)(u / (unsigned)kwords) * 32 + lane;
+        float v[32];
 #pragma unroll
-        for (int p = 0; p < NB; ++p) w[p][0] = w[p][1] = w[p][2] = w[p][3] = 0u;
+        for (int i = 0; i < 32; ++i) {
+            const int r = kw * 32 + i;
+            v[i] = (r < H && c < W) ? __ldg(x + (size_t)r * W + c) : 0.f;
+        }
+        uint32_t w[NB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const int r = kb * 128 + j * 32 + i;
-                float v = 0.f;
-                if (r < H && c < W) v = __ldg(x + (size_t)r * W + c);
-                const unsigned q = (unsigned)quantize_val(v, ub) & keep;
+        for (int p = 0; p < NB; ++p) w[p] = 0u;
 #pragma unroll
-                for (int p = 0; p < NB; ++p) w[p][j] |= ((q >> p) & 1u) << (31 - i);
-            }
+        for (int i = 0; i < 32; ++i) {
+            const unsigned q = (unsigned)quantize_val(v[i], ub) & keep;
+#pragma unroll
+            for (int p = 0; p < NB; ++p) w[p] |= ((q >> p) & 1u) << (31 - i);
         }
         if (c < col_limit) {
 #pragma unroll
             for (int p = 0; p < NB; ++p) {
-                const unsigned long long idx = (unsigned long long)p * plane + (unsigned long long)c * gdk * 4 + (unsigned long long)kb * 4;
-                if (idx + 4 <= out_words)  // C8 with P8(W) != P128(W): the reference writes out of bounds here; dropped
-                    *reinterpret_cast<uint4*>(out + idx) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+                const unsigned long long idx = (unsigned long long)p * plane + (unsigned long long)c * kwords + (unsigned long long)kw;
+                if (idx < out_words) out[idx] = w[p];  // C8 with P8(W) != P128(W): the reference writes out of bounds here; dropped
             }
         }
     }
@@ -167,6 +172,37 @@ __global__ void __launch_bounds__(256) count_nonzero_tiles_kernel(Words x1, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// Tile bitmap for zero-tile jumping in the tcgen05 engine: bit c of word w of tile (z, mt) is set iff the
+// 128-row x 128-bit block (rows 128mt.., K chunk 32w + c) of plane 0 of problem z has any bit set.
+// One warp per (z, mt, w): lane = chunk, 128 coalesced row reads, one ballot.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_bitmap_kernel(const uint32_t* __restrict__ x1, unsigned long long x1_words,
+                                                           unsigned long long bstride, int M, int K, int count,
+                                                           uint32_t* __restrict__ bitmap) {
+    const int lane = threadIdx.x & 31;
+    const int gdk = s128(K), mtiles = (p8(M) + 127) / 128, bmw = (gdk + 31) / 32;
+    const long long units = (long long)count * mtiles * bmw;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long gdk4 = (unsigned long long)gdk * 4;
+    for (long long u = warp_id; u < units; u += nwarps) {
+        const int w = (int)(u % bmw), mt = (int)((u / bmw) % mtiles), z = (int)(u / ((long long)bmw * mtiles));
+        const Words a{x1 + (unsigned long long)z * bstride, x1_words};
+        const int c = 32 * w + lane;
+        uint32_t any = 0;
+        if (c < gdk) {
+            const int r_end = min(128, p8(M) - mt * 128);
+            for (int r = 0; r < r_end; ++r) {
+                const uint4 v = ldw4(a, (unsigned long long)(mt * 128 + r) * gdk4 + 4ull * c);
+                any |= v.x | v.y | v.z | v.w;
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, any != 0u);
+        if (lane == 0) bitmap[u] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
 static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
@@ -179,12 +215,22 @@ static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
 
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st) {
     if (layout == QGTC_LAYOUT_ROW) {
-        const long long units = (long long)p8(H) * s128(W);
+        const int rows = p8(H), gdy = s128(W);
+        const long long units = (long long)rows * gdy;
         const long long blocks = (units + 8 * kPackUnroll - 1) / (8 * kPackUnroll);
         const int grid = grid_for(blocks, 8);
+        // warps sharing a row: only when there are fewer rows than warps
+        const long long nwarps = (long long)grid * 8;
+        int splits = 1;
+        if (rows < nwarps) {
+            splits = (int)(nwarps / rows);
+            const int max_splits = (gdy + kPackUnroll - 1) / kPackUnroll;
+            if (splits > max_splits) splits = max_splits;
+            if (splits < 1) splits = 1;
+        }
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
-        if (vec) pack_row_kernel<true><<<grid, 256, 0, st>>>(in, H, W, nbits, out);
-        else pack_row_kernel<false><<<grid, 256, 0, st>>>(in, H, W, nbits, out);
+        if (vec) pack_row_kernel<true><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
+        else pack_row_kernel<false><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
         note_launch();
         return check_launch("pack_row_kernel");
     }
@@ -194,7 +240,8 @@ int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_
         cudaError_t e = cudaMemsetAsync(out, 0, out_words * sizeof(uint32_t), st);
         if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(val2bit C8)");
     }
-    const long long units = (long long)s128(H) * ((col_limit + 31) >> 5);
+    const long long units = (long long)s128(H) * 4 * ((col_limit + 31) >> 5);
+    if (units >= (1ll << 31)) return QGTC_ERR_UNSUPPORTED;
     const int grid = grid_for((units + 7) / 8, 8);
 #define QGTC_PACK_COL(NB) \
     case NB: pack_col_kernel<NB><<<grid, 256, 0, st>>>(in, H, W, col_limit, out, (unsigned long long)out_words); break;
@@ -222,6 +269,14 @@ int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K
     count_nonzero_tiles_kernel<<<grid, 256, 0, st>>>(Words{x1, (unsigned long long)x1_words}, M, K, bit1, nz_dev);
     note_launch();
     return check_launch("count_nonzero_tiles_kernel");
+}
+
+int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int M, int K, int count, uint32_t* bitmap, cudaStream_t st) {
+    const long long units = (long long)count * ((p8(M) + 127) / 128) * ((s128(K) + 31) / 32);
+    const int grid = grid_for((units + 7) / 8, 8);
+    tile_bitmap_kernel<<<grid, 256, 0, st>>>(x1, (unsigned long long)x1_words, (unsigned long long)bstride, M, K, count, bitmap);
+    note_launch();
+    return check_launch("tile_bitmap_kernel");
 }
 
 }  // namespace qgtc

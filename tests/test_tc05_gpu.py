@@ -89,3 +89,45 @@ def test_tc05_unsupported_shapes_are_refused(capi):
     b = torch.zeros((2 * 4, 128), dtype=torch.int32, device="cuda")
     with pytest.raises(capi.QgtcError, match="unsupported"):
         capi.bitMM2Bit(a, b, 8, 8, 8, 2, 2, 2, engine=capi.ENGINE_TCGEN05)   # multi-bit A goes to the mma engine
+
+
+@pytest.mark.parametrize("M,K,N,b", [(1024, 1024, 64, 2), (1500, 2100, 16, 1), (4096, 4096, 64, 8), (700, 5000, 200, 4), (130, 16500, 32, 2)])
+def test_tile_bitmap_and_tilemap_gemm(capi, oracle, coracle, M, K, N, b):
+    """Precomputed tile bitmap (zero-tile jumping): bitmap == oracle, and the GEMM that skips the zero tiles is
+    bit-identical to the oracle GEMM."""
+    rng = np.random.default_rng(M + N)
+    A = np.zeros((M, K), np.float32)
+    for b0 in range(0, min(M, K), 128):                      # block-diagonal plus a few stray entries
+        A[b0:b0 + 128, b0:b0 + 128] = rng.random((min(128, M - b0), min(128, K - b0))) < 0.3
+    A[rng.integers(0, M, 20), rng.integers(0, K, 20)] = 1
+    if M > 300:
+        A[256:384, :] = 0                                    # one all-zero row tile
+    X = rand_features(rng, (K, N), b)
+    ba, bx = coracle.val2bit(A, 1, False, False), coracle.val2bit(X, b, True, False)
+    da, dx = dev_words(ba), dev_words(bx)
+    bm = capi.tile_bitmap(da, M, K)
+    want_bm = oracle.tile_bitmap(ba, M, K)
+    assert np.array_equal(bm.cpu().numpy().view(np.uint32).reshape(want_bm.shape), want_bm)
+    for eng in (capi.ENGINE_TCGEN05, capi.ENGINE_AUTO):
+        got = capi.bitMM2Bit_tilemap(da.view(1, -1), dx.view(1, -1), bm, 1, M, K, N, b, b, engine=eng)
+        assert np.array_equal(host_u32(got).reshape(-1), coracle.bitMM2Bit(ba, bx, M, K, N, 1, b, b).reshape(-1))
+        gi = capi.bitMM2Int_tilemap(da, dx, bm, M, K, N, b, True, engine=eng)
+        assert np.array_equal(gi.cpu().numpy(), coracle.bitMM2Int(ba, bx, M, K, N, 1, b, True))
+
+
+def test_tilemap_batched(capi, coracle):
+    M, K, N, b, cnt = 640, 896, 64, 2, 6
+    rng = np.random.default_rng(77)
+    adjs = []
+    for i in range(cnt):
+        a = rand_adj(rng, M, K, 0.002 if i % 2 else 0.3, zero_blocks=True)
+        if i == 3:
+            a[:] = 0                                          # an entirely empty graph
+        adjs.append(a)
+    x1 = np.stack([coracle.val2bit(a, 1, False, False).reshape(-1) for a in adjs])
+    x2 = np.stack([coracle.val2bit(rand_features(rng, (K, N), b), b, True, False).reshape(-1) for _ in range(cnt)])
+    d1, d2 = dev_words(x1), dev_words(x2)
+    bm = capi.tile_bitmap(d1, M, K, cnt)
+    out = capi.bitMM2Bit_tilemap(d1, d2, bm, cnt, M, K, N, b, b, engine=capi.ENGINE_TCGEN05)
+    for i in range(cnt):
+        assert np.array_equal(host_u32(out[i]).reshape(-1), coracle.bitMM2Bit(x1[i], x2[i], M, K, N, 1, b, b).reshape(-1)), i
