@@ -138,6 +138,14 @@ int qgtc_bitmm2bit_host(const int32_t* x1_host, size_t x1_words, const int32_t* 
                         int M, int K, int N, int bit1, int bit2, int out_bit,
                         int32_t* out_host, size_t out_words, int engine, unsigned flags, void* stream);
 
+/* Pipelined host-buffer form for a batch: the problems are processed in groups; the upload of group g+1 and the
+ * download of group g-1 overlap the GEMM of group g on library-owned streams (host buffers should be pinned for
+ * the copies to be asynchronous).  Synchronises before returning.  Same results as `count` calls of
+ * qgtc_bitmm2bit_host. */
+int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, const int32_t* x2_host, size_t x2_stride_words,
+                                int count, int M, int K, int N, int bit1, int bit2, int out_bit,
+                                int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream);
+
 /* Number of kernels this library has launched from the calling process (bench.py gpu_launches). */
 uint64_t qgtc_launch_count(void);
 

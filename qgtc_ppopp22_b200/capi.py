@@ -24,6 +24,7 @@ SYMBOLS = [
     "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
+    "qgtc_bitmm2bit_host_batched",
 ]
 
 _LIB = None
@@ -63,6 +64,7 @@ def lib() -> ctypes.CDLL:
         L.qgtc_bitmm2bit_batched.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2bit_host.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_launch_count.restype = c.c_uint64
+        L.qgtc_bitmm2bit_host_batched.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_tile_bitmap_words.restype = sz
         L.qgtc_tile_bitmap_words.argtypes = [i, i, i]
         L.qgtc_tile_bitmap.argtypes = [vp, sz, sz, i, i, i, vp, sz, vp]
@@ -231,4 +233,19 @@ def bitMM2Bit_host(x1_host: torch.Tensor, x2_host: torch.Tensor, M, K, N, bit1, 
         out_host = torch.empty(packed_shape(LAYOUT_ROW, out_bit, M, N), dtype=torch.int32).pin_memory()
     _check(lib().qgtc_bitmm2bit_host(x1_host.data_ptr(), x1_host.numel(), x2_host.data_ptr(), x2_host.numel(), M, K, N,
                                      bit1, bit2, out_bit, out_host.data_ptr(), out_host.numel(), engine, flags, _stream()), "bitMM2Bit_host")
+    return out_host
+
+
+def bitMM2Bit_host_batched(x1_host: torch.Tensor, x2_host: torch.Tensor, count, M, K, N, bit1, bit2, out_bit, out_host=None,
+                           engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """Pipelined host-buffer entry point: [count, words] pinned CPU tensors in, [count, words] CPU tensor out."""
+    for t, n in ((x1_host, "bit_X1"), (x2_host, "bit_X2")):
+        if t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous() or t.dim() != 2 or t.shape[0] != count:
+            raise QgtcError("%s must be a contiguous [count, words] int32 CPU tensor" % n)
+    wo = packed_words(LAYOUT_ROW, out_bit, M, N)
+    if out_host is None:
+        out_host = torch.empty((count, wo), dtype=torch.int32).pin_memory()
+    _check(lib().qgtc_bitmm2bit_host_batched(x1_host.data_ptr(), x1_host.shape[1], x2_host.data_ptr(), x2_host.shape[1], count, M, K, N,
+                                             bit1, bit2, out_bit, out_host.data_ptr(), out_host.shape[1], engine, flags, _stream()),
+           "bitMM2Bit_host_batched")
     return out_host

@@ -3,6 +3,7 @@
 // pack.cu, gemm_mma.cu and gemm_tc05.cu.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -317,6 +318,84 @@ int qgtc_bitmm2bit_host(const int32_t* x1_host, size_t x1_words, const int32_t* 
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return record_cuda_error(e, "D2H(bitmm2bit_host)");
     return QGTC_OK;
+}
+
+int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, const int32_t* x2_host, size_t x2_stride_words,
+                                int count, int M, int K, int N, int bit1, int bit2, int out_bit,
+                                int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream) {
+    if (!x1_host || !x2_host || !out_host || count <= 0) return QGTC_ERR_INVALID_ARG;
+    const size_t w1 = qgtc_packed_words(QGTC_LAYOUT_ROW, bit1, M, K);
+    const size_t w2 = qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N);
+    const size_t wo = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
+    if (!w1 || !w2 || !wo) return QGTC_ERR_INVALID_ARG;
+    if (x1_stride_words < w1 || x2_stride_words < w2 || out_stride_words < wo) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    cudaStream_t user = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+
+    // two slots of `group` problems each: upload(g+1) | gemm(g) | download(g-1)
+    int group = (int)((48u << 20) / ((w1 + w2 + wo) * 4));
+    if (group < 1) group = 1;
+    if (group > count) group = count;
+    if (group > 64) group = 64;
+    if (const char* ge = std::getenv("QGTC_HOST_GROUP")) {      // test hook: force small groups
+        const int v = std::atoi(ge);
+        if (v >= 1 && v < group) group = v;
+    }
+    const size_t slot_bytes = (((w1 + w2 + wo) * 4 * (size_t)group) + 255) & ~(size_t)255;
+    void* base = nullptr;
+    if (int rc = scratch_reserve(2 * slot_bytes, &base)) return rc;
+
+    static thread_local cudaStream_t s_up = nullptr, s_mm = nullptr, s_dn = nullptr;
+    static thread_local cudaEvent_t ev_up[2], ev_mm[2], ev_dn[2], ev_start;
+    static thread_local int streams_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (streams_dev != dev) {
+        cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s_mm, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_mm[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_dn[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+        streams_dev = dev;
+    }
+    // order after whatever the caller queued on its stream
+    cudaEventRecord(ev_start, user);
+    cudaStreamWaitEvent(s_up, ev_start, 0);
+    cudaStreamWaitEvent(s_mm, ev_start, 0);
+    cudaStreamWaitEvent(s_dn, ev_start, 0);
+
+    int rc = QGTC_OK;
+    const int ngroups = (count + group - 1) / group;
+    for (int g = 0; g < ngroups && rc == QGTC_OK; ++g) {
+        const int slot = g & 1, first = g * group, n = (count - first < group) ? count - first : group;
+        char* d1 = reinterpret_cast<char*>(base) + (size_t)slot * slot_bytes;
+        char* d2 = d1 + w1 * 4 * (size_t)group;
+        char* d3 = d2 + w2 * 4 * (size_t)group;
+        if (g >= 2) cudaStreamWaitEvent(s_up, ev_dn[slot], 0);      // the slot's previous results have left the device
+        cudaError_t e = cudaMemcpy2DAsync(d1, w1 * 4, x1_host + (size_t)first * x1_stride_words, x1_stride_words * 4, w1 * 4, n, cudaMemcpyHostToDevice, s_up);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(d2, w2 * 4, x2_host + (size_t)first * x2_stride_words, x2_stride_words * 4, w2 * 4, n, cudaMemcpyHostToDevice, s_up);
+        if (e != cudaSuccess) { rc = record_cuda_error(e, "H2D(bitmm2bit_host_batched)"); break; }
+        cudaEventRecord(ev_up[slot], s_up);
+        cudaStreamWaitEvent(s_mm, ev_up[slot], 0);
+        rc = qgtc_bitmm2bit_batched(reinterpret_cast<int32_t*>(d1), w1, reinterpret_cast<int32_t*>(d2), w2, n, M, K, N, bit1, bit2, out_bit,
+                                    reinterpret_cast<int32_t*>(d3), wo, engine, flags, s_mm);
+        if (rc != QGTC_OK) break;
+        cudaEventRecord(ev_mm[slot], s_mm);
+        cudaStreamWaitEvent(s_dn, ev_mm[slot], 0);
+        e = cudaMemcpy2DAsync(out_host + (size_t)first * out_stride_words, out_stride_words * 4, d3, wo * 4, wo * 4, n, cudaMemcpyDeviceToHost, s_dn);
+        if (e != cudaSuccess) { rc = record_cuda_error(e, "D2H(bitmm2bit_host_batched)"); break; }
+        cudaEventRecord(ev_dn[slot], s_dn);
+    }
+    cudaError_t e = cudaStreamSynchronize(s_dn);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s_mm);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s_up);
+    if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "sync(bitmm2bit_host_batched)");
+    return rc;
 }
 
 uint64_t qgtc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -224,6 +224,18 @@ def test_batched_and_host_entry_points(capi, coracle):
     ho = capi.bitMM2Bit_host(h1, h2, M, K, N, 1, b, b)
     assert np.array_equal(ho.numpy().view(np.uint32).reshape(-1), coracle.bitMM2Bit(x1[0], x2[0], M, K, N, 1, b, b).reshape(-1))
     assert capi.launch_count() > 0
+    # pipelined host-batched form: more problems than one group holds, ragged last group
+    cnt2 = 11
+    hx1 = torch.from_numpy(np.stack([x1[i % cnt] for i in range(cnt2)]).view(np.int32)).pin_memory()
+    hx2 = torch.from_numpy(np.stack([x2[i % cnt] for i in range(cnt2)]).view(np.int32)).pin_memory()
+    import os
+    os.environ["QGTC_HOST_GROUP"] = "4"            # 3 groups, the last one ragged
+    try:
+        hob = capi.bitMM2Bit_host_batched(hx1, hx2, cnt2, M, K, N, 1, b, b)
+    finally:
+        del os.environ["QGTC_HOST_GROUP"]
+    for i in range(cnt2):
+        assert np.array_equal(hob[i].numpy().view(np.uint32), coracle.bitMM2Bit(x1[i % cnt], x2[i % cnt], M, K, N, 1, b, b).reshape(-1)), i
 
 
 def test_tile_counts(capi, oracle):
