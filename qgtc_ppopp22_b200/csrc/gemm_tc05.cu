@@ -366,10 +366,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         // wch chunks; the 16 warps form G = 16 / wpi groups that take the items round-robin, so a warp
         // has G item periods to get through its (latency-bound) wait / expand / store / signal chain.
         const int q = warp & 3, t = warp >> 2;
-        const int WCH = T.wch, spi = T.wpi >> 2, G = kProducerWarps / T.wpi;
+        // G <= S is required: a warp that reaches item X has seen the MMAs of item X-G-S complete (it waited for
+        // them at item X-G), which only implies that item X-2S is done -- no mbarrier phase aliasing -- if G <= S.
+        const int WCH = T.wch, spi = T.wpi >> 2;
+        const int G = min(min(kProducerWarps / T.wpi, S), kRawSlots);
         const int g = t / spi, c0 = (t - g * spi) * WCH;
         const int row = 32 * q + lane;             // row of the tile == TMEM lane
-        const int my_items = (n_items - g + G - 1) / G;
+        const int my_items = g < G ? (n_items - g + G - 1) / G : 0;   // warps beyond the last group idle
         // byte offsets of this warp's 16-byte chunks of the row inside a raw slot, with the TMA swizzle
         // (Swizzle<log2(cps),4,3>: address bits [4,4+log2 cps) ^= bits [7,7+log2 cps))
         uint32_t off[2];
@@ -399,32 +402,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[slot]);       // the slot can be refilled while we expand
             if (tr) QGTC_TRACE(0, k, 1);
-            mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
-            tc_fence_after();
-            if (tr) QGTC_TRACE(0, k, 3);
+            // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
+            // stage's previous use drain, so only the tcgen05.st sits behind the wait
             unsigned nzmask = 0;
+            auto expand = [&](const uint4& pv, uint32_t (&r)[32]) -> bool {
+                const bool nz = nojump || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
+                if (nz) {
+                    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (j < WCH) {   // warp-uniform
-                    const bool nz = nojump || __any_sync(0xffffffffu, (v[j].x | v[j].y | v[j].z | v[j].w) != 0u);
-                    uint32_t r[32];
-                    if (nz) {
-                        nzmask |= 1u << j;
-                        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    for (int ks = 0; ks < 4; ++ks) {
+                        r[ks * 8] = w[ks] & 0x01010101u;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            r[ks * 8] = w[ks] & 0x01010101u;
-#pragma unroll
-                            for (int cidx = 1; cidx < 8; ++cidx)
-                                r[ks * 8 + cidx] = (use_mulhi ? __umulhi(w[ks], mult[cidx]) : (w[ks] >> cidx)) & 0x01010101u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) r[e] = 0u;
+                        for (int cidx = 1; cidx < 8; ++cidx)
+                            r[ks * 8 + cidx] = (use_mulhi ? __umulhi(w[ks], mult[cidx]) : (w[ks] >> cidx)) & 0x01010101u;
                     }
-                    if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols + j * 32), r);
-                    else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) r[e] = 0u;
                 }
+                return nz;
+            };
+            {
+                uint32_t r[32];
+                if (expand(v[0], r)) nzmask |= 1u;
+                if (tr) QGTC_TRACE(0, k, 2);
+                mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
+                tc_fence_after();
+                if (tr) QGTC_TRACE(0, k, 3);
+                if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols), r);
+                else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
+            }
+            if (WCH > 1) {   // warp-uniform
+                uint32_t r[32];
+                if (expand(v[1], r)) nzmask |= 2u;
+                if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols + 32), r);
+                else if (r[5] == 0xdeadbeefu) flags[255] = 1;
             }
             if (tr) QGTC_TRACE(0, k, 4);
             if (!dbg_no_st) tmem_wait_st();
@@ -721,6 +733,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.cps = 256 / T.NP;
     if (T.cps > kMaxCps) T.cps = kMaxCps;
     if (T.cps < 1) T.cps = 1;
+    static const int cps_cap = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
+    if (cps_cap && T.cps > cps_cap) T.cps = cps_cap;       // experiment knob: shallower stages, deeper ring
     if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
     T.nst = (a.gdk + T.cps - 1) / T.cps;
     T.wch = T.cps == 4 ? 2 : 1;
