@@ -59,6 +59,7 @@ typedef enum qgtc_gemm_engine {
 /* flags for the GEMM entry points */
 #define QGTC_FLAG_NO_ZERO_JUMP 0x1u /* do not skip all-zero adjacency tiles (for A/B timing)        */
 #define QGTC_FLAG_COL_REF_QUIRK 0x2u /* bitmm2bit_col: reproduce the shipped kernel's stores exactly */
+#define QGTC_FLAG_TC05_PAIR 0x4u    /* tcgen05 engine: 2-CTA clusters, tcgen05.mma.cta_group::2 (M = 256)  */
 
 int qgtc_abi_version(void);
 const char* qgtc_strerror(int status);

@@ -15,7 +15,7 @@ import torch
 from . import lib_dir
 
 ENGINE_AUTO, ENGINE_MMA_SYNC, ENGINE_TCGEN05 = 0, 1, 2
-FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK = 0x1, 0x2
+FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK, FLAG_TC05_PAIR = 0x1, 0x2, 0x4
 LAYOUT_ROW, LAYOUT_COL128, LAYOUT_COL8 = 0, 1, 2
 
 # every symbol include/qgtc_b200.h declares (checked by tests/test_abi.py)

@@ -57,6 +57,8 @@ struct Tc05Args {
     int dbufs;                      // accumulator buffers (1 or 2)
     int mtiles;                     // 128-row tiles per problem
     int total_tiles;                // count * mtiles
+    int units;                      // work units: tiles, or 256-row super-tiles in pair mode (count * ceil(mtiles / 2))
+    int spg;                        // pair mode: super-tiles per problem
     int epi;
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
@@ -140,6 +142,46 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// ---- 2-CTA ("pair") forms: one tcgen05.mma.cta_group::2 covers 256 rows (128 per CTA) with each CTA holding half
+// of the B columns; issued by the leader CTA (cluster rank 0) only.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+}
+// commit that arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_i8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA's shared memory
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
 // SS form (A from shared memory); only used by a timing experiment
 __device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -205,23 +247,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, both K-major, M = 128.
-__host__ __device__ constexpr uint32_t make_idesc_i8(int n) {
-    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_i8(int n, int m = 128) {
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | (((uint32_t)m >> 4) << 24);
 }
 
 struct SmemLayout {
     // offsets in bytes from the 1024-byte aligned base
     int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps) {
+__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, int pair = 0) {
     SmemLayout L;
     L.raw0 = 0;
     L.raw_slot_bytes = 128 * 16 * cps;                 // 2/4/8 KB, keeps every slot 1024-byte aligned for the swizzle
     if (L.raw_slot_bytes < 1024) L.raw_slot_bytes = 1024;
     L.b_stage0 = L.raw0 + kRawSlots * L.raw_slot_bytes;
-    L.b_stage_bytes = cps * NP * 128;
+    L.b_stage_bytes = cps * NP * (pair ? 64 : 128);    // pair mode: each CTA holds half of the feature columns
     L.bars = L.b_stage0 + stages * L.b_stage_bytes;
-    L.flags = L.bars + (2 * kMaxStages + 2 * kRawSlots + 4) * 8;
+    L.flags = L.bars + (3 * kMaxStages + 2 * kRawSlots + 6) * 8;
     L.misc = L.flags + kMaxStages * 16;
     L.total = L.misc + 32;
     return L;
@@ -258,12 +300,36 @@ __device__ __forceinline__ uint32_t tile_word(const uint32_t* bm_tile, int w, in
     return bm_tile ? (__ldg(bm_tile + w) & valid) : valid;
 }
 
+// Work-unit geometry.  Without pairing a unit is one 128-row tile; in pair mode it is a 256-row super-tile whose
+// halves go to the two CTAs of the cluster (the second half may lie beyond the matrix: TMA then reads zeros and the
+// epilogue writes nothing).
+struct UnitGeo {
+    int z, mt;          // problem, this CTA's 128-row tile
+};
+template <bool PAIR>
+__device__ __forceinline__ UnitGeo unit_geo(const Tc05Args& T, int u, int rank) {
+    UnitGeo g;
+    if (PAIR) { g.z = u / T.spg; g.mt = 2 * (u - g.z * T.spg) + rank; }
+    else      { g.z = u / T.mtiles; g.mt = u - g.z * T.mtiles; }
+    return g;
+}
+// chunk bits of word w of a unit (pair: OR of both tiles, so that both CTAs walk the same stages)
+template <bool PAIR>
+__device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, int gdk) {
+    if (!T.bitmap) return tile_word(nullptr, w, gdk);
+    if (!PAIR) return tile_word(T.bitmap + (size_t)u * T.bmw, w, gdk);
+    const int z = u / T.spg, mt0 = 2 * (u - z * T.spg);
+    uint32_t r = tile_word(T.bitmap + ((size_t)z * T.mtiles + mt0) * T.bmw, w, gdk);
+    if (mt0 + 1 < T.mtiles) r |= tile_word(T.bitmap + ((size_t)z * T.mtiles + mt0 + 1) * T.bmw, w, gdk);
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Feature image: X2 (packed planes, raw words, zero-extension) -> u8 values in the MMA's K order,
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP) {
+__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves) {
     const int gdk = P.gdk, n_lim = p8(P.N);
     const long long per_problem = (long long)gdk * NP * 4;  // (chunk, n, s)
     const long long total = per_problem * P.count;
@@ -281,17 +347,19 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
                 for (int j = 0; j < 8; ++j) o[j] |= ((w >> j) & 0x01010101u) << q;
             }
         }
-        uint8_t* dst = img + (unsigned long long)z * gstride + (unsigned long long)c * NP * 128 +
-                       (unsigned long long)(2 * s) * (NP / 8) * 128 + (unsigned long long)(n >> 3) * 128 + (n & 7) * 16;
+        // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
+        const int nh = NP / halves, h = n / nh, nl = n - h * nh;
+        uint8_t* dst = img + (unsigned long long)z * gstride + (unsigned long long)c * NP * 128 + (unsigned long long)h * nh * 128 +
+                       (unsigned long long)(2 * s) * (nh / 8) * 128 + (unsigned long long)(nl >> 3) * 128 + (nl & 7) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(dst + (NP / 8) * 128) = make_uint4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<uint4*>(dst + (nh / 8) * 128) = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // The GEMM kernel
 // ---------------------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
@@ -299,7 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     const GemmArgs& P = T.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps, nst = T.nst;
-    const SmemLayout L = smem_layout(NP, S, CPS);
+    const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0);
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;            // 0 = leader (issues the MMAs)
+    const int group_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int ngroups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     unsigned char* raw_slots = smem_raw + L.raw0;
     unsigned char* b_stages = smem_raw + L.b_stage0;
@@ -309,7 +380,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     uint64_t* raw_full = bars + 2 * kMaxStages;     // [kRawSlots]  adjacency TMA -> expanders
     uint64_t* raw_empty = raw_full + kRawSlots;     // [kRawSlots]  4 expander warps -> adjacency loader
     uint64_t* d_full = raw_empty + kRawSlots;       // [2] MMA -> epilogue   (count 2: one commit per issuer)
-    uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 4 warps)
+    uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 8 warps)
+    uint64_t* peer_full = d_empty + 2;              // [kMaxStages] pair mode, leader only: the peer CTA's stage is ready (relayed)
+    uint64_t* peer_dempty = peer_full + kMaxStages; // [2]          pair mode, leader only: the peer's epilogue drained the accumulator
     volatile unsigned char* flags = smem_raw + L.flags;  // [stage][chunk][lane quarter]: that expander warp's 32 x 128 bits are non-zero
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.misc);
 
@@ -325,34 +398,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 2);
             mbar_init(&d_empty[b], kEpilogueWarps);
+            mbar_init(&peer_dempty[b], 1);
         }
+        for (int s = 0; s < kMaxStages; ++s) mbar_init(&peer_full[s], 1);
         fence_mbar_init();
     }
     if (warp == kALoaderWarp && lane == 0) prefetch_tmap(&tmapA);
-    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kMmaWarp) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
+    }
     // number of pipeline items of this CTA = non-zero stages of its tiles (all stages without a bitmap)
     int* item_count = reinterpret_cast<int*>(smem_raw + L.misc + 16);
     if (threadIdx.x == 0) *item_count = 0;
     __syncthreads();
     {
-        const int tiles_here = (T.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int units_here = (T.units - group_id + ngroups - 1) / ngroups;
         int cnt = 0;
-        for (int i = threadIdx.x; i < tiles_here * T.bmw; i += blockDim.x) {
-            const int tl = i / T.bmw, w = i - tl * T.bmw;
-            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
-            cnt += __popc(stage_bits(tile_word(bm_tile, w, P.gdk), T.cps));
+        for (int i = threadIdx.x; i < units_here * T.bmw; i += blockDim.x) {
+            const int ul = i / T.bmw, w = i - ul * T.bmw;
+            cnt += __popc(stage_bits(unit_word<PAIR>(T, group_id + ul * ngroups, w, P.gdk), T.cps));
         }
         if (cnt) atomicAdd(item_count, cnt);
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything is signalled across
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int dcols = T.dbufs * NP;       // accumulators first, then the A stages (32 columns per chunk)
     const int stage_cols = CPS * 32;
 
-    const int my_tiles = (T.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (T.units - group_id + ngroups - 1) / ngroups;   // work units of this CTA (pair)
     const int n_items = *item_count;      // launch_gemm_tc05 guarantees this fits 31 bits
     const bool nojump = (P.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
@@ -458,13 +535,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             int slot = 0;
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                int z = tile / T.mtiles;
-                const int row0 = (tile - z * T.mtiles) * 128;
-                if (!T.a_batched) z = 0;
-                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                const int u = group_id + tl * ngroups;
+                const UnitGeo ug = unit_geo<PAIR>(T, u, rank);
+                const int z = T.a_batched ? ug.z : 0;
+                const int row0 = ug.mt * 128;                // may lie beyond the matrix in pair mode: TMA fills zeros
                 for (int w = 0; w < T.bmw; ++w) {
-                    uint32_t m = stage_bits(tile_word(bm_tile, w, gdk), CPS);
+                    uint32_t m = stage_bits(unit_word<PAIR>(T, u, w, gdk), CPS);
                     while (m) {
                         const int c0 = 32 * w + __ffs(m) - 1;   // first chunk of a non-zero stage
                         m &= m - 1;
@@ -483,11 +559,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             int s = 0;
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const uint8_t* img = T.bimg + (unsigned long long)(tile / T.mtiles) * T.bimg_gstride;
-                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                const int u = group_id + tl * ngroups;
+                const uint8_t* img = T.bimg + (unsigned long long)unit_geo<PAIR>(T, u, rank).z * T.bimg_gstride;
                 for (int w = 0; w < T.bmw; ++w) {
-                    uint32_t m = stage_bits(tile_word(bm_tile, w, gdk), CPS);
+                    uint32_t m = stage_bits(unit_word<PAIR>(T, u, w, gdk), CPS);
                     while (m) {
                         const int c0 = 32 * w + __ffs(m) - 1;
                         m &= m - 1;
@@ -495,6 +570,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
                         if (dbg_no_bulk) {
                             mbar_arrive(&full[s]);
+                        } else if (PAIR) {
+                            // this CTA's half of every chunk (the image keeps the two halves of a chunk apart)
+                            const uint32_t half_bytes = chunk_bytes >> 1;
+                            mbar_expect_tx(&full[s], half_bytes * (uint32_t)nch);
+                            for (int j = 0; j < nch; ++j)
+                                bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes + (size_t)j * half_bytes,
+                                         img + (unsigned long long)(c0 + j) * chunk_bytes + (unsigned long long)rank * half_bytes, half_bytes, &full[s]);
                         } else {
                             mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
                             bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
@@ -512,7 +594,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         // leaves the accumulator zeroed), so the order between the two issuers does not matter.
         // Each warp runs with warp-uniform state (addresses and descriptors live in uniform registers);
         // one elected lane issues the tcgen05 instructions.
-        {
+        if (PAIR && rank != 0) {
+            // ---- peer CTA of a pair: it issues no MMAs.  Its two otherwise idle issuer warps relay "this CTA's
+            // stage is ready" (warp 25) and "this CTA's epilogue has drained the accumulator" (warp 27) to the leader.
+            if (lane == 0) {
+                if (warp == kMmaWarp) {
+                    int s = 0;
+                    uint32_t use = 0;
+                    for (int it = 0; it < n_items; ++it) {
+                        mbar_wait(&full[s], use & 1, T.error_flag, 9);
+                        tc_fence_after();
+                        tc_fence_before();
+                        mbar_arrive_leader(&peer_full[s]);
+                        if (++s == S) { s = 0; ++use; }
+                    }
+                } else {
+                    int buf = 0;
+                    uint32_t duse = 0;
+                    for (int tl = 0; tl < my_tiles; ++tl) {
+                        mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 10);
+                        tc_fence_after();
+                        tc_fence_before();
+                        mbar_arrive_leader(&peer_dempty[buf]);
+                        if (++buf == T.dbufs) { buf = 0; ++duse; }
+                    }
+                }
+            }
+        } else {
             const int who = warp == kMmaWarp ? 0 : 1;
             // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; using the
             // literal keeps every MMA operand provably warp-uniform (uniform registers, no per-MMA R2UR).
@@ -521,14 +629,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 __trap();
             }
             const uint32_t tb = 0u;
-            const uint32_t idesc = make_idesc_i8(NP);
-            const uint32_t lbo = (uint32_t)(NP / 8) * 128u, sbo = 128u;
+            const uint32_t idesc = make_idesc_i8(NP, PAIR ? 256 : 128);
+            const uint32_t lbo = (uint32_t)(NP / (PAIR ? 16 : 8)) * 128u, sbo = 128u;   // pair: this CTA's smem holds NP/2 columns
             // descriptor = constant high word | (low word that only differs in the 14-bit start address)
             const uint64_t desc0 = make_smem_desc(smem_u32(b_stages), lbo, sbo);
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
             const uint32_t lo0 = (uint32_t)desc0;
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
-            const uint32_t chunk_lo = ((uint32_t)NP * 128u) >> 4;
+            const uint32_t chunk_lo = ((uint32_t)NP * (PAIR ? 64u : 128u)) >> 4;
             const uint32_t kstep_lo = (2u * lbo) >> 4;
             // chunks [jlo, jhi) of a stage belong to this issuer
             const int half = CPS >> 1;
@@ -538,6 +646,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             uint32_t use = 0, duse = 0;
             auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
                 mbar_wait(&full[s_], use_ & 1, T.error_flag, 4);
+                if (PAIR) {   // ... and the peer CTA's half of the stage; its zero flags are not visible here: issue everything
+                    mbar_wait(&peer_full[s_], use_ & 1, T.error_flag, 11);
+                    tc_fence_after();
+                    return dbg_no_mma ? 0u : 0xFu;
+                }
                 tc_fence_after();
                 // one word per chunk: the four lane quarters' "non-zero" bytes
                 const uint32_t w = lane < 4 ? *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 16 + lane * 4) : 0u;
@@ -546,12 +659,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             };
             for (int tl = 0; tl < my_tiles; ++tl) {
                 mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 3);   // the epilogue has drained and zeroed this accumulator
+                if (PAIR) mbar_wait(&peer_dempty[buf], duse & 1, T.error_flag, 12);
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const uint32_t* bm_tile = T.bitmap ? T.bitmap + (size_t)tile * T.bmw : nullptr;
+                const int u = group_id + tl * ngroups;
                 for (int bw = 0; bw < T.bmw; ++bw) {
-                  uint32_t sm = stage_bits(tile_word(bm_tile, bw, gdk), CPS);
+                  uint32_t sm = stage_bits(unit_word<PAIR>(T, u, bw, gdk), CPS);
                   for (; sm; sm &= sm - 1, ++item) {
                     const int c_first = 32 * bw + __ffs(sm) - 1;       // first chunk of this non-zero stage
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 0);
@@ -568,18 +681,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                    mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                    if (PAIR) mma_i8_ts_pair(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                    else mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
                                 }
                             }
                         }
                     }
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 2);
-                    if (elect_one()) tc_commit(&empty[s]);   // arrives when this issuer's MMAs have finished reading A (TMEM) and B (smem)
+                    if (elect_one()) {   // arrives when this issuer's MMAs have finished reading A (TMEM) and B (smem); pair: in both CTAs
+                        if (PAIR) tc_commit_pair(&empty[s]);
+                        else tc_commit(&empty[s]);
+                    }
                     if (lane == 0 && who == 0) QGTC_TRACE(1, item, 3);
                     if (++s == S) { s = 0; ++use; }
                   }
                 }
-                if (elect_one()) tc_commit(&d_full[buf]);    // arrives when this issuer's share of the accumulator is complete
+                if (elect_one()) {   // arrives when this issuer's share of the accumulator is complete
+                    if (PAIR) tc_commit_pair(&d_full[buf]);
+                    else tc_commit(&d_full[buf]);
+                }
                 if (++buf == T.dbufs) { buf = 0; ++duse; }
             }
         }
@@ -613,8 +733,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             if (lane == 0) mbar_arrive(&d_empty[b]);
         }
         for (int tl = 0; tl < my_tiles; ++tl) {
-            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int z = tile / T.mtiles, m = (tile - z * T.mtiles) * 128 + 32 * q + lane;
+            const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
+            const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
             mbar_wait(&d_full[buf], duse & 1, T.error_flag, 6);
             tc_fence_after();
@@ -683,10 +803,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA may retire (or free its TMEM) while the other can still touch it
+    else __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -742,11 +864,18 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
     int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
-    while (stages > 2 && smem_layout(T.NP, stages, T.cps).total > 200 * 1024) --stages;
+    static const bool pair_env = [] { const char* e = getenv("QGTC_TC05_PAIR"); return e && e[0] == '1'; }();
+    // pair mode (opt-in: QGTC_FLAG_TC05_PAIR or QGTC_TC05_PAIR=1): two CTAs of a cluster share every MMA
+    // (cta_group::2, M = 256) and each streams half of the feature image.  Measured on B200 it does not beat the
+    // single-CTA form (the adjacency expanders, not the tensor front end or L2, bound the kernel): DESIGN.md 5.4.
+    const bool pair = (pair_env || (a.flags & QGTC_FLAG_TC05_PAIR)) && (T.NP % 16 == 0) && ((long long)((p8(a.M) + 127) / 128) * a.count >= 2);
+    while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
     T.mtiles = (p8(a.M) + 127) / 128;
     T.total_tiles = T.mtiles * a.count;
+    T.spg = (T.mtiles + 1) / 2;
+    T.units = pair ? T.spg * a.count : T.total_tiles;
     T.epi = epi;
     T.one = 1u;
     T.bitmap = a.tile_bitmap;
@@ -809,21 +938,35 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     const long long prep_items = (long long)a.gdk * T.NP * 4 * img_problems;
     long long pgrid = (prep_items + 255) / 256;
     if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, 0, st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP);
+    prep_b_kernel<<<(int)pgrid, 256, 0, st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1);
     note_launch();
     int rc = check_launch("prep_b_kernel");
 
     if (rc == QGTC_OK) {
-        const int smem = smem_layout(T.NP, T.stages, T.cps).total + 1024;
-        const int grid = T.total_tiles < kNumSMs ? T.total_tiles : kNumSMs;
+        const int smem = smem_layout(T.NP, T.stages, T.cps, pair).total + 1024;
+        const int groups = pair ? (T.units < kNumSMs / 2 ? T.units : kNumSMs / 2) : (T.units < kNumSMs ? T.units : kNumSMs);
         auto launch = [&](auto kfn) -> int {
             cudaError_t e2 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaFuncSetAttribute(gemm_tc05)");
-            kfn<<<grid, kThreads, smem, st>>>(T, tmap);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(pair ? 2 * groups : groups);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = pair ? 2 : 1;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e2 = cudaLaunchKernelEx(&cfg, kfn, T, tmap);
             note_launch();
+            if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
             return check_launch("gemm_tc05_kernel");
         };
-        rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat>) : launch(gemm_tc05_kernel<kEpiBitsRow>);
+        if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, true>);
+        else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, false>);
     }
     e = cudaFreeAsync(img, st);
     if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "cudaFreeAsync(feature image)");

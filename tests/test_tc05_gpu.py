@@ -49,6 +49,9 @@ def test_tc05_bitmm2bit_and_int(capi, coracle, M, K, N, b2, ob):
     assert np.array_equal(g8.cpu().numpy(), coracle.bitMM2Int(ba, bx8, M, K, N, 1, b2, False))
     # the two engines agree with each other as well
     assert torch.equal(capi.bitMM2Bit(da, dx, M, K, N, 1, b2, ob, engine=capi.ENGINE_MMA_SYNC), got)
+    # 2-CTA cluster form (tcgen05.mma.cta_group::2): same bits
+    assert torch.equal(capi.bitMM2Bit(da, dx, M, K, N, 1, b2, ob, engine=E, flags=capi.FLAG_TC05_PAIR), got)
+    assert torch.equal(capi.bitMM2Int(da, dx, M, K, N, 1, b2, True, engine=E, flags=capi.FLAG_TC05_PAIR), gi)
 
 
 @pytest.mark.parametrize("b", [1, 2, 4, 8])
@@ -82,6 +85,8 @@ def test_tc05_batched(capi, coracle):
     out = capi.bitMM2Bit_batched(dev_words(x1), dev_words(x2), cnt, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
     for i in range(cnt):
         assert np.array_equal(host_u32(out[i]).reshape(-1), coracle.bitMM2Bit(x1[i], x2[i], M, K, N, 1, b, b).reshape(-1)), i
+    pair = capi.bitMM2Bit_batched(dev_words(x1), dev_words(x2), cnt, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05, flags=capi.FLAG_TC05_PAIR)
+    assert torch.equal(pair, out)
 
 
 def test_tc05_unsupported_shapes_are_refused(capi):
@@ -129,5 +134,6 @@ def test_tilemap_batched(capi, coracle):
     d1, d2 = dev_words(x1), dev_words(x2)
     bm = capi.tile_bitmap(d1, M, K, cnt)
     out = capi.bitMM2Bit_tilemap(d1, d2, bm, cnt, M, K, N, b, b, engine=capi.ENGINE_TCGEN05)
+    assert torch.equal(capi.bitMM2Bit_tilemap(d1, d2, bm, cnt, M, K, N, b, b, engine=capi.ENGINE_TCGEN05, flags=capi.FLAG_TC05_PAIR), out)
     for i in range(cnt):
         assert np.array_equal(host_u32(out[i]).reshape(-1), coracle.bitMM2Bit(x1[i], x2[i], M, K, N, 1, b, b).reshape(-1)), i
