@@ -92,18 +92,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU (each failed try_wait has slept up to ~10 ms).
+// Bounded wait: a protocol bug must not hang the GPU.  `backoff_ns` > 0 puts the warp to sleep between polls: roles
+// with long expected waits (epilogue, loaders) must not steal issue slots from the expanders -- the scheduler
+// favours high warp ids, and a failed try_wait comes back after only ~50-100 cycles.
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* error_flag, int where) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 400u) {
+        if (kBackoffNs > 0) __nanosleep(kBackoffNs);
+        if (++spins > (1u << 24)) {
             if (error_flag) atomicExch(error_flag, 0x80000000u | (unsigned)where);
             __trap();
         }
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 uint32_t r[32];
                 if (expand(v[0], r)) nzmask |= 1u;
                 if (tr) QGTC_TRACE(0, k, 2);
-                mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
+                mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
                 tc_fence_after();
                 if (tr) QGTC_TRACE(0, k, 3);
                 if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols), r);
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     while (m) {
                         const int c0 = 32 * w + __ffs(m) - 1;   // first chunk of a non-zero stage
                         m &= m - 1;
-                        mbar_wait(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8);
+                        mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8);
                         mbar_expect_tx(&raw_full[slot], bytes);
                         tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
                         if (++slot == kRawSlots) { slot = 0; ++use; }
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         const int c0 = 32 * w + __ffs(m) - 1;
                         m &= m - 1;
                         const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
-                        mbar_wait(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
+                        mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
                         if (dbg_no_bulk) {
                             mbar_arrive(&full[s]);
                         } else if (PAIR) {
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     int s = 0;
                     uint32_t use = 0;
                     for (int it = 0; it < n_items; ++it) {
-                        mbar_wait(&full[s], use & 1, T.error_flag, 9);
+                        mbar_wait<64>(&full[s], use & 1, T.error_flag, 9);
                         tc_fence_after();
                         tc_fence_before();
                         mbar_arrive_leader(&peer_full[s]);
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     int buf = 0;
                     uint32_t duse = 0;
                     for (int tl = 0; tl < my_tiles; ++tl) {
-                        mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 10);
+                        mbar_wait<256>(&d_empty[buf], duse & 1, T.error_flag, 10);
                         tc_fence_after();
                         tc_fence_before();
                         mbar_arrive_leader(&peer_dempty[buf]);
@@ -736,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
             const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
-            mbar_wait(&d_full[buf], duse & 1, T.error_flag, 6);
+            mbar_wait<256>(&d_full[buf], duse & 1, T.error_flag, 6);
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
             const bool valid = true;
