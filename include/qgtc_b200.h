@@ -123,6 +123,13 @@ int qgtc_bitmm2int_tilemap(const int32_t* x1_dev, size_t x1_words, const int32_t
                            const uint32_t* bitmap_dev, int M, int K, int N, int bit2, int pad128,
                            float* out_dev, size_t out_elems, int engine, unsigned flags, void* stream);
 
+/* Packed 1-bit adjacency R(1,H,W) directly from an edge list (int32 row / column indices on the device): the
+ * result equals qgtc_val2bit of the dense 0/1 matrix with ones at the listed positions (duplicates collapse,
+ * out-of-range edges are ignored), without materialising the dense fp32 H x W matrix the reference builds
+ * (sampler.py:87-89, torch.sparse...to_dense()). */
+int qgtc_edges2bit(const int32_t* rows_dev, const int32_t* cols_dev, size_t n_edges, int H, int W,
+                   int32_t* out_dev, size_t out_words, void* stream);
+
 /* Batched bit-GEMM: `count` independent problems of identical shape, one launch (persistent CTAs).
  * Problem i uses x1 + i*x1_stride_words, x2 + i*x2_stride_words, out + i*out_stride_words.
  * This is the throughput form of bitMM2Bit_profile (QGTC_device.cu:379-434: 200 back-to-back

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
-    "qgtc_bitmm2bit_host_batched",
+    "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit",
 ]
 
 _LIB = None
@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
         L.qgtc_bitmm2bit_host.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_launch_count.restype = c.c_uint64
         L.qgtc_bitmm2bit_host_batched.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_edges2bit.argtypes = [vp, vp, sz, i, i, vp, sz, vp]
         L.qgtc_tile_bitmap_words.restype = sz
         L.qgtc_tile_bitmap_words.argtypes = [i, i, i]
         L.qgtc_tile_bitmap.argtypes = [vp, sz, sz, i, i, i, vp, sz, vp]
@@ -249,3 +250,14 @@ def bitMM2Bit_host_batched(x1_host: torch.Tensor, x2_host: torch.Tensor, count, 
                                              bit1, bit2, out_bit, out_host.data_ptr(), out_host.shape[1], engine, flags, _stream()),
            "bitMM2Bit_host_batched")
     return out_host
+
+
+def edges2bit(rows: torch.Tensor, cols: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Packed 1-bit adjacency R(1,H,W) from int32 edge endpoints on the device (== val2bit of the dense 0/1 matrix)."""
+    _req_cuda(rows, torch.int32, "rows"); _req_cuda(cols, torch.int32, "cols")
+    if rows.numel() != cols.numel():
+        raise QgtcError("rows and cols must have the same length")
+    with torch.cuda.device(rows.device):
+        out = torch.empty(packed_shape(LAYOUT_ROW, 1, H, W), dtype=torch.int32, device=rows.device)
+        _check(lib().qgtc_edges2bit(rows.data_ptr(), cols.data_ptr(), rows.numel(), H, W, out.data_ptr(), out.numel(), _stream()), "edges2bit")
+    return out

@@ -118,7 +118,8 @@ class ClusterIter:
     """
 
     def __init__(self, dn, g: SyntheticGraph, psize, batch_size, seed_nid=None, use_pp=False, regular=False,
-                 bit_width=2, run_GIN=False, device=None, batch_ids=None, keep_on_cpu=False, ops=None, par_li=None):
+                 bit_width=2, run_GIN=False, device=None, batch_ids=None, keep_on_cpu=False, ops=None, par_li=None,
+                 from_edges=False):
         self.g = g
         self.psize = psize
         self.batch_size = batch_size
@@ -159,10 +160,16 @@ class ClusterIter:
             rows = torch.from_numpy(local_id[es[starts[cid]:starts[cid + 1]]])
             cols = torch.from_numpy(local_id[ed[starts[cid]:starts[cid + 1]]])
             self.batch_edges[cid] = (rows, cols)
-            A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
-            A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
             X = g.feat[torch.from_numpy(nodes)].to(self.device)
-            bit_A = ops.val2bit(A, 1, False, False)
+            if from_edges:
+                # extension: pack the adjacency straight from the edge list (no dense fp32 n x n intermediate)
+                from . import capi
+                bit_A = capi.edges2bit(rows.to(self.device, torch.int32), cols.to(self.device, torch.int32), n, n)
+                A = None
+            else:
+                A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+                A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
+                bit_A = ops.val2bit(A, 1, False, False)
             bit_X = ops.val2bit(X, self.bit_width, True, False)
             if keep_on_cpu:
                 bit_A, bit_X = bit_A.cpu(), bit_X.cpu()

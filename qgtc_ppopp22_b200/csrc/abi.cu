@@ -15,6 +15,7 @@ namespace qgtc {
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st);
 int launch_bit2val(const uint32_t* in, size_t in_words, int nbits, int H, int W, int col_major, int* out, cudaStream_t st);
 int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K, int bit1, unsigned long long* nz_dev, cudaStream_t st);
+int launch_edges_to_bits(const int* rows, const int* cols, long long n_edges, int H, int W, uint32_t* out, size_t out_words, cudaStream_t st);
 int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int M, int K, int count, uint32_t* bitmap, cudaStream_t st);
 int launch_gemm_mma(const GemmArgs& a, int epi, cudaStream_t st);
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st);   // QGTC_ERR_UNSUPPORTED when the shape does not qualify
@@ -223,6 +224,16 @@ int qgtc_bitmm2bit_batched(const int32_t* x1_dev, size_t x1_stride_words, const 
     a.out_bstride = out_stride_words;
     if (int rc = check_device()) return rc;
     return run_gemm(a, kEpiBitsRow, engine, (cudaStream_t)stream);
+}
+
+int qgtc_edges2bit(const int32_t* rows_dev, const int32_t* cols_dev, size_t n_edges, int H, int W,
+                   int32_t* out_dev, size_t out_words, void* stream) {
+    if (!out_dev || H <= 0 || W <= 0 || (n_edges && (!rows_dev || !cols_dev))) return QGTC_ERR_INVALID_ARG;
+    if (!aligned16(out_dev)) return QGTC_ERR_ALIGNMENT;
+    const size_t need = qgtc_packed_words(QGTC_LAYOUT_ROW, 1, H, W);
+    if (out_words < need) return QGTC_ERR_SIZE;
+    if (int rc = check_device()) return rc;
+    return launch_edges_to_bits(rows_dev, cols_dev, (long long)n_edges, H, W, reinterpret_cast<uint32_t*>(out_dev), need, (cudaStream_t)stream);
 }
 
 size_t qgtc_tile_bitmap_words(int M, int K, int count) {

@@ -203,6 +203,19 @@ __global__ void __launch_bounds__(256) tile_bitmap_kernel(const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// Batch construction straight from an edge list: packed 1-bit adjacency R(1, n, n) without the dense fp32
+// n x n intermediate the reference materialises (sampler.py:87-89).  One thread per edge, atomicOr of a bit.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) edges_to_bits_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long n_edges,
+                                                             int H, int W, uint32_t* __restrict__ out) {
+    const size_t wpr = (size_t)s128(W) * 4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(rows + e), c = __ldg(cols + e);
+        if (r >= 0 && r < H && c >= 0 && c < W) atomicOr(out + (size_t)r * wpr + (c >> 5), 1u << (31 - (c & 31)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
 static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
@@ -269,6 +282,18 @@ int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K
     count_nonzero_tiles_kernel<<<grid, 256, 0, st>>>(Words{x1, (unsigned long long)x1_words}, M, K, bit1, nz_dev);
     note_launch();
     return check_launch("count_nonzero_tiles_kernel");
+}
+
+int launch_edges_to_bits(const int* rows, const int* cols, long long n_edges, int H, int W, uint32_t* out, size_t out_words, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out, 0, out_words * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(edges2bit)");
+    if (n_edges > 0) {
+        const int grid = grid_for((n_edges + 255) / 256, 8);
+        edges_to_bits_kernel<<<grid, 256, 0, st>>>(rows, cols, n_edges, H, W, out);
+        note_launch();
+        return check_launch("edges_to_bits_kernel");
+    }
+    return QGTC_OK;
 }
 
 int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int M, int K, int count, uint32_t* bitmap, cudaStream_t st) {

@@ -63,3 +63,37 @@ def test_epoch_runner_eager_and_graph():
     r3 = drv.run(a, graph=g, quiet=True)
     assert r1["batches"] == 3 and r1["epoch_ms"] > 0 and r2["epoch_ms"] > 0 and r3["epoch_ms"] > 0
     assert r1["checksum"] == r2["checksum"] == r3["checksum"]
+
+
+def test_cluster_iter_from_edges_matches_dense_path():
+    import qgtc_ppopp22_b200
+    from qgtc_ppopp22_b200 import cluster as C
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    g = C.make_synthetic_graph("tiny", 60)
+    par = C.shuffled_partitions(g, 60)
+    a = C.ClusterIter("tiny", g, 60, 20, None, bit_width=2, ops=QGTC, par_li=par)
+    b = C.ClusterIter("tiny", g, 60, 20, None, bit_width=2, ops=QGTC, par_li=par, from_edges=True)
+    for (ca, _), (cb, _) in zip(a, b):
+        assert torch.equal(ca.bit_A, cb.bit_A) and torch.equal(ca.bit_X, cb.bit_X)
+
+
+def test_gcnconv_qnt_matches_integer_math(oracle):
+    """The layer API with matching layouts: logits equal the exact integer pipeline on the quantized values."""
+    from qgtc_ppopp22_b200.QGTC_conv import GCNConv_Qnt
+    torch.manual_seed(0)
+    n, D, h, C, wb, ab = 300, 40, 16, 10, 2, 3
+    A = (torch.rand(n, n) < 0.03).float().cuda()
+    X = (torch.rand(n, D) * 9 - 0.5).cuda()
+    m = GCNConv_Qnt(D, h, C, w_bit=wb, act_bit=ab).cuda()
+    with torch.no_grad():
+        m.W_in.copy_(torch.rand(D, h) * 5 - 0.5)
+        m.W_out.copy_(torch.rand(h, C) * 5 - 0.5)
+    got = m(A, X).cpu().numpy()
+    q = lambda t, b: (oracle.quantize_val(t.detach().cpu().numpy(), b) & ((1 << b) - 1)).astype(np.int64)
+    An, Xq, W1, W2 = A.cpu().numpy().astype(np.int64), q(X, ab), q(m.W_in, wb), q(m.W_out, wb)
+    mask = (1 << ab) - 1
+    xw = oracle.requantize(Xq @ W1, ab) & mask
+    hq = oracle.requantize(An @ xw, ab) & mask
+    hw = oracle.requantize(hq @ W2, ab) & mask
+    want = (An @ hw).astype(np.float32)
+    assert got.shape == (n, C) and np.array_equal(got, want)

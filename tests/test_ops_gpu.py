@@ -305,3 +305,20 @@ def test_non_default_stream_and_async(capi, oracle):
     want = oracle.bitMM2Bit(ba, bx, M, K, N, 1, b, b)
     for o in outs:
         assert np.array_equal(host_u32(o), want)
+
+
+@pytest.mark.parametrize("H,W,E", [(759, 759, 11000), (130, 513, 900), (3, 3, 5), (2258, 2258, 40000), (64, 4100, 0)])
+def test_edges2bit_equals_dense_pack(capi, oracle, H, W, E):
+    """Edge list -> packed adjacency == val2bit of the dense 0/1 matrix (duplicates collapse, bad edges ignored)."""
+    rng = np.random.default_rng(H + E)
+    rows = rng.integers(0, H, E).astype(np.int32)
+    cols = rng.integers(0, W, E).astype(np.int32)
+    if E > 10:
+        rows[:3], cols[:3] = rows[3:6], cols[3:6]           # duplicates
+        rows[6], cols[7] = -1, W + 5                        # out of range: ignored
+    A = np.zeros((H, W), np.float32)
+    ok = (rows >= 0) & (rows < H) & (cols >= 0) & (cols < W)
+    A[rows[ok], cols[ok]] = 1
+    got = capi.edges2bit(torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), H, W)
+    want = oracle.val2bit(A, 1, False, False)
+    assert tuple(got.shape) == want.shape and np.array_equal(host_u32(got), want)
