@@ -44,7 +44,7 @@ if __name__ == "__main__":
             G = min(G, 512)
             for b in (1, 2, 4, 8):
                 try:
-                    ms, tops = run(e, M, M, N, b, G)
+                    ms, tops = run(e, M, M, N, b, G, flags=int(os.environ.get("QGTC_SWEEP_FLAGS", "0"), 0))
                     print(json.dumps({"engine": name, "M": M, "K": M, "N": N, "bits": b, "graphs": G, "ms": round(ms, 4), "tops": round(tops, 1)}), flush=True)
                 except Exception as ex:
                     print(json.dumps({"engine": name, "M": M, "N": N, "bits": b, "error": str(ex)[:200]}), flush=True)

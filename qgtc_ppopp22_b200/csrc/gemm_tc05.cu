@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
     const bool dbg_no_st = (P.flags & 0x10000u) != 0, dbg_no_mma = (P.flags & 0x20000u) != 0;
     const bool dbg_no_bulk = (P.flags & 0x40000u) != 0, dbg_no_ldg = (P.flags & 0x80000u) != 0;
-    const bool use_mulhi = (P.flags & 0x100000u) == 0;
+    const bool use_mulhi = (P.flags & 0x100000u) != 0;   // experiment knob: mul.hi on the FMA pipe instead of a shift (measured slower)
 
     if (warp < kProducerWarps) {
         // ===================== adjacency expanders =====================
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             o ^= ((o >> 7) & (uint32_t)(CPS - 1)) << 4;
             off[j] = o;
         }
-        // multipliers 2^(32-c): mul.hi gives w >> c on the FMA pipe, leaving only the mask for the ALU pipe
+        // multipliers 2^(32-c) for the mul.hi variant of the expansion (knob; the plain shift measured 8 % faster)
         uint32_t mult[8];
 #pragma unroll
         for (int c = 1; c < 8; ++c) mult[c] = T.one << (32 - c);
@@ -843,9 +843,10 @@ bool tc05_supports(const GemmArgs& a, int epi) {
     if (a.bit1 != 1) return false;                 // the expanders handle a single adjacency plane
     if (p8(a.N) > 256) return false;               // one MMA N block
     if (!a_in_bounds(a) || !encode_tiled_fn()) return false;
-    // worth it only when there is enough work to amortise the feature-image prepass
+    // measured single-call latency (profiles/r1_single_call_sweep.txt): tcgen05 wins from ~0.04 GOP up
+    // (e.g. 2258 x 2258 x 16: 11.7 us vs 20.8 us); below that the two launches and the pipeline prologue cost more
     const double ops = 2.0 * a.M * (double)a.K * a.N * a.count;
-    return ops >= 2.0e9;
+    return ops >= 4.0e7;
 }
 
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
