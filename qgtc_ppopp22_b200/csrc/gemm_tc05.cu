@@ -334,29 +334,39 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves) {
-    const int gdk = P.gdk, n_lim = p8(P.N);
-    const long long per_problem = (long long)gdk * NP * 4;  // (chunk, n, s)
-    const long long total = per_problem * P.count;
+    // One block per (problem, K chunk).  Phase 1 stages the chunk's packed words (bit2 planes x NP columns x 4 words)
+    // in shared memory as [plane][word][column]; phase 2 has consecutive threads produce consecutive columns, so the
+    // 16-byte stores of a warp are one contiguous 512-byte run of the image.
+    extern __shared__ uint32_t pk[];   // [bit2][4][NP]
+    const int gdk = P.gdk, n_lim = p8(P.N), bit2 = P.bit2;
     const unsigned long long gdk4 = (unsigned long long)gdk * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i / per_problem);
-        const long long r = i % per_problem;
-        const int s = (int)(r & 3), n = (int)((r >> 2) % NP), c = (int)((r >> 2) / NP);
+    const int nh = NP / halves;
+    for (long long blk = blockIdx.x; blk < (long long)P.count * gdk; blk += gridDim.x) {
+        const int z = (int)(blk / gdk), c = (int)(blk - (long long)z * gdk);
         const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
-        uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (n < n_lim) {
-            for (int q = 0; q < P.bit2; ++q) {
-                const uint32_t w = ldw(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * c + s);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] |= ((w >> j) & 0x01010101u) << q;
-            }
+        for (int i = threadIdx.x; i < bit2 * NP; i += blockDim.x) {
+            const int q = i / NP, n = i - q * NP;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * c);
+            uint32_t* dst = pk + (size_t)q * 4 * NP + n;
+            dst[0] = w.x; dst[NP] = w.y; dst[2 * NP] = w.z; dst[3 * NP] = w.w;
         }
-        // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
-        const int nh = NP / halves, h = n / nh, nl = n - h * nh;
-        uint8_t* dst = img + (unsigned long long)z * gstride + (unsigned long long)c * NP * 128 + (unsigned long long)h * nh * 128 +
-                       (unsigned long long)(2 * s) * (nh / 8) * 128 + (unsigned long long)(nl >> 3) * 128 + (nl & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(dst + (nh / 8) * 128) = make_uint4(o[4], o[5], o[6], o[7]);
+        __syncthreads();
+        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c * NP * 128;
+        for (int i = threadIdx.x; i < 8 * NP; i += blockDim.x) {   // item = (k group 0..7, column n), n fastest
+            const int kg = i / NP, n = i - kg * NP, s = kg >> 1, j0 = (kg & 1) * 4;
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            for (int q = 0; q < bit2; ++q) {
+                const uint32_t w = pk[(size_t)(q * 4 + s) * NP + n];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] |= ((w >> (j0 + j)) & 0x01010101u) << q;
+            }
+            // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
+            const int h = n / nh, nl = n - h * nh;
+            *reinterpret_cast<uint4*>(base + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
+                make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
     }
 }
 
@@ -940,10 +950,9 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
 
     GemmArgs pa = a;
     pa.count = img_problems;
-    const long long prep_items = (long long)a.gdk * T.NP * 4 * img_problems;
-    long long pgrid = (prep_items + 255) / 256;
+    long long pgrid = (long long)a.gdk * img_problems;
     if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, 0, st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1);
+    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * 4 * T.NP * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1);
     note_launch();
     int rc = check_launch("prep_b_kernel");
 
