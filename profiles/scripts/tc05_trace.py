@@ -21,25 +21,29 @@ if __name__ == "__main__":
     flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 0
     ms, tops = run(capi.ENGINE_TCGEN05, 4096, 4096, N, 2, 128, reps=1, flags=flags)
     print("ms", ms, "tops", tops)
-    buf = np.zeros(3 * 512 * 8, dtype=np.uint64)
+    buf = np.zeros(8 * 512 * 8, dtype=np.uint64)
     L = capi.lib()
     L.qgtc_debug_tc05_trace.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     n = L.qgtc_debug_tc05_trace(buf.ctypes.data, buf.size)
-    t = buf.reshape(3, 512, 8).astype(np.int64)
+    t = buf.reshape(8, 512, 8).astype(np.int64)
     t0 = t[1, 0, 0]
     prod, mma, epi = t[0], t[1], t[2]
-    print("MMA issuer: item  issue(chunks 0-2)  acquire_next  issue(last)+commit  | loop period")
-    for i in range(20, 44):
-        r = mma[i]
-        print("  %3d  %6d %6d %6d | %6d   (t=%d)" % (i, r[1] - r[0], r[2] - r[1], r[3] - r[2], mma[i + 1][0] - r[0], r[0] - t0))
-    print("producer warp 0: item  cpwait+lds  fetch  wait_empty  expand+st  wait_st  arrive | period")
-    for i in range(10, 24):
-        r = prod[i]
-        print("  %3d  %6d %6d %6d %6d %6d %6d | %6d  (t=%d)" % (i, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], prod[i + 1][0] - r[0], r[0] - t0))
+    for role, name in ((1, "MMA issuer 0"), (5, "MMA issuer 1")):
+        mm = t[role]
+        print(name + " (own items): item  wait_full  flags+ballot  issue+commit | (t_start)")
+        for i in range(20, 36):
+            r = mm[i]
+            if r[0]:
+                print("  %3d  %6d %6d %6d |  (t=%d)" % (i, r[4] - r[0], r[1] - r[4], r[3] - r[1], r[0] - t0))
+    for role, name in ((0, "expander warp 0 (group 0, SMSP0)"), (3, "expander warp 1 (group 0, SMSP1)"), (4, "expander warp 3 (group 0, SMSP3)"), (6, "expander warp 8 (group 1, SMSP0)")):
+        pr = t[role]
+        print(name + " own items: rawwait+lds  expand0  wait_empty  st+expand1+st  wait_st  flags+arrive | period (t_start, t_arrive)")
+        for i in range(10, 20):
+            r = pr[i]
+            print("  %3d  %6d %6d %6d %6d %6d %6d | %6d  (%d, %d)" % (i, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], pr[i + 1][0] - r[0], r[0] - t0, r[6] - t0))
     print("epilogue warp 8: tile  wait_dfull  work | period")
     for i in range(0, 6):
         r = epi[i]
         print("  %3d  %7d %7d | %7d" % (i, r[1] - r[0], r[2] - r[1], epi[i + 1][0] - r[0]))
-    for name, a, k in (("mma period", mma, 0), ("producer period", prod, 0)):
-        d = np.diff(a[8:200, k])
-        print(name, "mean", d.mean(), "median", np.median(d))
+    d = np.diff(prod[8:100, 0])
+    print("expander own-item period: mean", d.mean(), "median", np.median(d))

@@ -35,10 +35,11 @@ constexpr int kProducerWarps = 16;
 constexpr int kEpilogueWarp0 = 16;
 constexpr int kEpilogueWarps = 8;
 constexpr int kLoaderWarp = 24;
-constexpr int kMmaWarp = 25;
-constexpr int kALoaderWarp = 26;
-constexpr int kMmaWarp2 = 27;     // second MMA issuer: takes the upper half of every stage's chunks
-constexpr int kThreads = 28 * 32;
+constexpr int kALoaderWarp = 25;
+constexpr int kMmaWarp = 26;      // first MMA issuer (also allocates TMEM); issuer i is warp kMmaWarp + i
+constexpr int kMaxIssuers = 4;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
+constexpr int kMmaWarp2 = kMmaWarp + 1;
+constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
 constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
 constexpr int kMaxStages = 4;
 constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
@@ -63,6 +64,7 @@ struct Tc05Args {
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
     int bmw;                        // bitmap words per tile = ceil(gdk / 32)
+    int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
     unsigned int* error_flag;       // device word set by the watchdog
     unsigned long long* trace;      // optional clock64 trace of CTA 0 (QGTC_TC05_TRACE=1), else null
@@ -70,7 +72,7 @@ struct Tc05Args {
 constexpr int kTraceItems = 512;    // per role: [item][8] timestamps
 #define QGTC_TRACE(role, item, slot)                                                             \
     do {                                                                                         \
-        if (T.trace && blockIdx.x == 0 && (item) < kTraceItems)                                  \
+        if (DBG && T.trace && blockIdx.x == 0 && (item) < kTraceItems)                           \
             T.trace[((role) * kTraceItems + (item)) * 8 + (slot)] = (unsigned long long)clock64(); \
     } while (0)
 
@@ -99,16 +101,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  `backoff_ns` > 0 puts the warp to sleep between polls: roles
-// with long expected waits (epilogue, loaders) must not steal issue slots from the expanders -- the scheduler
-// favours high warp ids, and a failed try_wait comes back after only ~50-100 cycles.
+// try_wait with a suspend-time hint: the thread may stay suspended (no issue slots used) until the phase
+// completes or the hint expires
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  Two forms, chosen by `hinted`:
+//  - hinted: try_wait with a long suspend-time hint and no sleep;
+//  - else `kBackoffNs` > 0 puts the warp to sleep between polls: roles with long expected waits (epilogue,
+//    loaders) must not steal issue slots from the expanders -- the scheduler favours high warp ids, and a
+//    failed plain try_wait comes back after only ~50-100 cycles.
 template <int kBackoffNs = 0>
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* error_flag, int where) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* error_flag, int where, bool hinted = false) {
     uint32_t spins = 0;
+    if (hinted) {   // a failed hinted try_wait sleeps on the barrier (NANOSLEEP.SYNCS), so the bound is generous in time
+        while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+            if (++spins > (1u << 22)) {
+                if (error_flag) { atomicExch_system(error_flag, 0x80000000u | (unsigned)where); __threadfence_system(); }
+                __trap();
+            }
+        }
+        return;
+    }
     while (!mbar_try_wait(bar, parity)) {
         if (kBackoffNs > 0) __nanosleep(kBackoffNs);
         if (++spins > (1u << 24)) {
-            if (error_flag) atomicExch(error_flag, 0x80000000u | (unsigned)where);
+            if (error_flag) { atomicExch_system(error_flag, 0x80000000u | (unsigned)where); __threadfence_system(); }
             __trap();
         }
     }
@@ -373,8 +399,62 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
 // ---------------------------------------------------------------------------------------------
 // The GEMM kernel
 // ---------------------------------------------------------------------------------------------
-template <int EPI, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
+// Requantize + plane-pack epilogue of one accumulator tile for one warp (bitMM2Bit): the warp owns TMEM lane
+// quarter q (one row per lane) and every other 32-column word.  OB > 0 fixes the number of output planes at
+// compile time; OB == 0 takes it from `ob_rt`.
+template <int OB>
+__device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half, int N, int ob_rt, int dshift, uint32_t rmask, bool row_ok,
+                                              uint32_t* out_row, unsigned long long opt_offset) {
+    constexpr int kPlanes = OB > 0 ? OB : 8;
+    const int ob = OB > 0 ? OB : ob_rt;
+    const unsigned keep = (1u << ob) - 1u;
+    const int mx = 1 << ob;
+    uint32_t pw[kPlanes];
+#pragma unroll
+    for (int p = 0; p < kPlanes; ++p) pw[p] = 0u;
+    for (int cb = 0; cb < NP / 16; ++cb) {
+        if (((cb >> 1) & 1) != half) continue;
+        int v[16];
+        tmem_ld16(d_tmem + 16 * cb, v);
+        // rows past M and columns past N contribute zero bits: one byte mask per four values
+        const bool whole = 16 * cb + 16 <= N;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+            uint32_t four = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int acc = v[4 * g4 + e] >> dshift;
+                const int rq = acc > mx ? mx - 1 : (acc < 0 ? 1 : acc);   // reference kernel.h:31-37
+                four |= ((uint32_t)rq & keep) << (8 * e);
+            }
+            uint32_t mask = rmask;
+            if (!whole) {
+                const int nv = N - (16 * cb + 4 * g4);   // valid columns of this group of four
+                mask = nv >= 4 ? rmask : (nv <= 0 ? 0u : (rmask & ((1u << (8 * nv)) - 1u)));
+            }
+            four &= mask;
+            const int nib_pos = 28 - 4 * (((16 * cb + 4 * g4) & 31) >> 2);
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p)
+                if (p < ob) pw[p] |= nibble_of_plane(four, p) << nib_pos;
+        }
+        if ((cb & 1) || cb == NP / 16 - 1) {   // a 32-column word is complete (or the tile ends on a half word)
+            const int w = cb >> 1;
+            if (row_ok) {
+#pragma unroll
+                for (int p = 0; p < kPlanes; ++p)
+                    if (p < ob) out_row[(unsigned long long)p * opt_offset + w] = pw[p];
+            }
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p) pw[p] = 0u;
+        }
+    }
+}
+
+// DBG = true adds the clock64 trace and the timing-experiment knobs (flag bits 0x10000..0x200000); the production
+// instance carries none of that code in its (latency-bound) role loops.
+template <int EPI, bool PAIR, bool DBG>
+__global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -403,14 +483,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&full[s], T.wpi + 1);         // the expander warps of one item + the feature copy's expect_tx
-            mbar_init(&empty[s], 2);                // both MMA issuers commit
+            mbar_init(&empty[s], T.ni);             // every MMA issuer commits every item (see the issuer loop)
         }
         for (int s = 0; s < kRawSlots; ++s) {
             mbar_init(&raw_full[s], 1);
             mbar_init(&raw_empty[s], T.wpi);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&d_full[b], 2);
+            mbar_init(&d_full[b], T.ni);     // every issuer commits its share of the tile
             mbar_init(&d_empty[b], kEpilogueWarps);
             mbar_init(&peer_dempty[b], 1);
         }
@@ -447,9 +527,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     const int n_items = *item_count;      // launch_gemm_tc05 guarantees this fits 31 bits
     const bool nojump = (P.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
-    const bool dbg_no_st = (P.flags & 0x10000u) != 0, dbg_no_mma = (P.flags & 0x20000u) != 0;
-    const bool dbg_no_bulk = (P.flags & 0x40000u) != 0, dbg_no_ldg = (P.flags & 0x80000u) != 0;
-    const bool use_mulhi = (P.flags & 0x100000u) != 0;   // experiment knob: mul.hi on the FMA pipe instead of a shift (measured slower)
+    const bool dbg_no_st = DBG && (P.flags & 0x10000u) != 0, dbg_no_mma = DBG && (P.flags & 0x20000u) != 0;
+    const bool dbg_no_bulk = DBG && (P.flags & 0x40000u) != 0, dbg_no_ldg = DBG && (P.flags & 0x80000u) != 0;
+    // Scaled expansion (default): adjacency bit c of every byte is moved to the byte's MSB by an integer multiply
+    // (FMA pipe) and one AND (ALU pipe), so the A operand holds 0x80 instead of 1 and the accumulators hold
+    // 128 x the true sums; the epilogue shifts them back (exact).  The launcher clears this when
+    // K * (2^bit2 - 1) * 128 could reach 2^31; then bits are moved to bit 0 by a shift + AND (both ALU pipe).
+    const bool scaled = (P.flags & 0x100000u) == 0;
+    const bool hinted = !DBG || (P.flags & 0x200000u) == 0;      // knob set: mbarrier waits poll with nanosleep back-off instead of a suspend hint
 
     if (warp < kProducerWarps) {
         // ===================== adjacency expanders =====================
@@ -473,74 +558,91 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             o ^= ((o >> 7) & (uint32_t)(CPS - 1)) << 4;
             off[j] = o;
         }
-        // multipliers 2^(32-c) for the mul.hi variant of the expansion (knob; the plain shift measured 8 % faster)
+        // multipliers 2^(7-c) of the scaled expansion; derived from a kernel argument so that ptxas keeps them
+        // as IMAD operands (FMA pipe) instead of folding them back into ALU-pipe shifts
         uint32_t mult[8];
 #pragma unroll
-        for (int c = 1; c < 8; ++c) mult[c] = T.one << (32 - c);
-        mult[0] = 0;
+        for (int c = 0; c < 8; ++c) mult[c] = T.one << (7 - c);
 
         int slot = g % kRawSlots, s = g % S;       // raw ring slot and TMEM/B stage of the current item
         uint32_t raw_use = (uint32_t)(g / kRawSlots), use = (uint32_t)(g / S);
         const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + c0 * 32);
-        for (int k = 0; k < my_items; ++k) {
-            const bool tr = (warp == 0 && lane == 0);
-            if (tr) QGTC_TRACE(0, k, 0);
-            if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7);
-            uint4 v[2];
-            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes;
-            v[0] = *reinterpret_cast<const uint4*>(src + off[0]);
-            v[1] = WCH > 1 ? *reinterpret_cast<const uint4*>(src + off[1]) : make_uint4(0u, 0u, 0u, 0u);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[slot]);       // the slot can be refilled while we expand
-            if (tr) QGTC_TRACE(0, k, 1);
-            // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
-            // stage's previous use drain, so only the tcgen05.st sits behind the wait
-            unsigned nzmask = 0;
-            auto expand = [&](const uint4& pv, uint32_t (&r)[32]) -> bool {
-                const bool nz = nojump || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
-                if (nz) {
-                    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+        // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
+        const int trole = warp == 0 ? 0 : (warp == 1 ? 3 : (warp == 3 ? 4 : (warp == 8 ? 6 : -1)));
+        const bool tr = DBG && (trole >= 0 && lane == 0);
+        const bool two = WCH > 1;
+        volatile unsigned char* my_flags = flags + c0 * 4 + q;
+        auto expand = [&](const uint4& pv, uint32_t (&r)[32]) -> bool {
+            const bool nz = nojump || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
+            if (nz) {
+                const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+                if (scaled) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (int cidx = 0; cidx < 7; ++cidx) r[ks * 8 + cidx] = (w[ks] * mult[cidx]) & 0x80808080u;
+                        r[ks * 8 + 7] = w[ks] & 0x80808080u;
+                    }
+                } else {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         r[ks * 8] = w[ks] & 0x01010101u;
 #pragma unroll
-                        for (int cidx = 1; cidx < 8; ++cidx)
-                            r[ks * 8 + cidx] = (use_mulhi ? __umulhi(w[ks], mult[cidx]) : (w[ks] >> cidx)) & 0x01010101u;
+                        for (int cidx = 1; cidx < 8; ++cidx) r[ks * 8 + cidx] = (w[ks] >> cidx) & 0x01010101u;
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) r[e] = 0u;
                 }
-                return nz;
-            };
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) r[e] = 0u;
+            }
+            return nz;
+        };
+        for (int k = 0; k < my_items; ++k) {
+            if (tr) QGTC_TRACE(trole, k, 0);
+            if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7, hinted);
+            uint4 v[2];
+            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes;
+            v[0] = *reinterpret_cast<const uint4*>(src + off[0]);
+            v[1] = two ? *reinterpret_cast<const uint4*>(src + off[1]) : make_uint4(0u, 0u, 0u, 0u);
+            if (tr) QGTC_TRACE(trole, k, 1);
+            // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
+            // stage's previous use drain, so only the tcgen05.st sits behind the wait
+            unsigned nzmask = 0;
+            const uint32_t st_s = st_addr + (uint32_t)(s * stage_cols);
             {
                 uint32_t r[32];
                 if (expand(v[0], r)) nzmask |= 1u;
-                if (tr) QGTC_TRACE(0, k, 2);
-                mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1);   // the MMAs of the previous use of this stage are done
+                if (tr) QGTC_TRACE(trole, k, 2);
+                mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
                 tc_fence_after();
-                if (tr) QGTC_TRACE(0, k, 3);
-                if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols), r);
+                if (tr) QGTC_TRACE(trole, k, 3);
+                if (!dbg_no_st) tmem_st32(st_s, r);
                 else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
             }
-            if (WCH > 1) {   // warp-uniform
+            if (two) {   // warp-uniform
                 uint32_t r[32];
                 if (expand(v[1], r)) nzmask |= 2u;
-                if (!dbg_no_st) tmem_st32(st_addr + (uint32_t)(s * stage_cols + 32), r);
+                if (!dbg_no_st) tmem_st32(st_s + 32u, r);
                 else if (r[5] == 0xdeadbeefu) flags[255] = 1;
             }
-            if (tr) QGTC_TRACE(0, k, 4);
+            // every lane holds its raw words by now (the votes of the expansions needed them): the slot can be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[slot]);
+            if (tr) QGTC_TRACE(trole, k, 4);
             if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
-            if (tr) QGTC_TRACE(0, k, 5);
-            if (lane < WCH) flags[s * 16 + (c0 + lane) * 4 + q] = (unsigned char)((nzmask >> lane) & 1u);
-            __syncwarp();
+            if (tr) QGTC_TRACE(trole, k, 5);
+            if (lane == 0) {
+                my_flags[s * 16] = (unsigned char)(nzmask & 1u);
+                if (two) my_flags[s * 16 + 4] = (unsigned char)((nzmask >> 1) & 1u);
+            }
+            __syncwarp();   // every lane's tcgen05.st has completed
             if (lane == 0) mbar_arrive(&full[s]);
-            if (tr) QGTC_TRACE(0, k, 6);
+            if (tr) QGTC_TRACE(trole, k, 6);
             slot += G;
-            while (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
+            if (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
             s += G;
-            while (s >= S) { s -= S; ++use; }
+            if (s >= S) { s -= S; ++use; }
         }
     } else if (warp == kALoaderWarp) {
         // ===================== adjacency TMA loader =====================
@@ -558,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     while (m) {
                         const int c0 = 32 * w + __ffs(m) - 1;   // first chunk of a non-zero stage
                         m &= m - 1;
-                        mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8);
+                        mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8, hinted);
                         mbar_expect_tx(&raw_full[slot], bytes);
                         tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
                         if (++slot == kRawSlots) { slot = 0; ++use; }
@@ -581,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                         const int c0 = 32 * w + __ffs(m) - 1;
                         m &= m - 1;
                         const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
-                        mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2);
+                        mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);
                         if (dbg_no_bulk) {
                             mbar_arrive(&full[s]);
                         } else if (PAIR) {
@@ -600,12 +702,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 }
             }
         }
-    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+    } else if (warp >= kMmaWarp) {
         // ===================== MMA issuers =====================
-        // Two warps issue: a tcgen05.mma of 128 x 64 x 32 keeps the tensor pipe busy ~32 cycles but one
-        // warp sustains only one issue per ~65 cycles.  Issuer 0 takes chunks [0, cps/2) of every stage,
-        // issuer 1 the rest (with cps == 1 they alternate stages).  Every MMA accumulates (the epilogue
-        // leaves the accumulator zeroed), so the order between the two issuers does not matter.
+        // T.ni warps issue: a tcgen05.mma of 128 x 64 x 32 keeps the tensor pipe busy ~32 cycles, but one
+        // warp needs ~1300 cycles of (latency-bound) instruction stream per item: wait, flags, 16 MMAs with their
+        // descriptors, commit.  The issuers take the items round-robin.  Every MMA accumulates (the epilogue
+        // leaves the accumulator zeroed), so the order between the issuers does not matter.
+        // Protocol: EVERY issuer waits for EVERY item's `full` phase and commits to its `empty` barrier (count
+        // T.ni); only the owner issues MMAs in between.  A non-owner's commit tracks the MMAs of its own earlier
+        // items, so "item i is done" implies "all earlier items are done" (the expanders' phase arithmetic needs
+        // that order), and no issuer ever skips a phase of a barrier it waits on (mbarrier waits only see parity).
         // Each warp runs with warp-uniform state (addresses and descriptors live in uniform registers);
         // one elected lane issues the tcgen05 instructions.
         if (PAIR && rank != 0) {
@@ -616,17 +722,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                     int s = 0;
                     uint32_t use = 0;
                     for (int it = 0; it < n_items; ++it) {
-                        mbar_wait<64>(&full[s], use & 1, T.error_flag, 9);
+                        mbar_wait<64>(&full[s], use & 1, T.error_flag, 9, hinted);
                         tc_fence_after();
                         tc_fence_before();
                         mbar_arrive_leader(&peer_full[s]);
                         if (++s == S) { s = 0; ++use; }
                     }
-                } else {
+                } else if (warp == kMmaWarp2) {
                     int buf = 0;
                     uint32_t duse = 0;
                     for (int tl = 0; tl < my_tiles; ++tl) {
-                        mbar_wait<256>(&d_empty[buf], duse & 1, T.error_flag, 10);
+                        mbar_wait<256>(&d_empty[buf], duse & 1, T.error_flag, 10, hinted);
                         tc_fence_after();
                         tc_fence_before();
                         mbar_arrive_leader(&peer_dempty[buf]);
@@ -635,11 +741,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 }
             }
         } else {
-            const int who = warp == kMmaWarp ? 0 : 1;
+            const int who = warp - kMmaWarp;
+            const int trole = who == 0 ? 1 : (who == 1 ? 5 : -1);   // traced issuers
             // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; using the
             // literal keeps every MMA operand provably warp-uniform (uniform registers, no per-MMA R2UR).
             if (tmem_base != 0u) {
-                if (T.error_flag) atomicExch(T.error_flag, 0x40000000u | tmem_base);
+                if (T.error_flag) { atomicExch_system(T.error_flag, 0x40000000u | tmem_base); __threadfence_system(); }
                 __trap();
             }
             const uint32_t tb = 0u;
@@ -652,16 +759,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
             const uint32_t chunk_lo = ((uint32_t)NP * (PAIR ? 64u : 128u)) >> 4;
             const uint32_t kstep_lo = (2u * lbo) >> 4;
-            // chunks [jlo, jhi) of a stage belong to this issuer
-            const int half = CPS >> 1;
-            const int jlo = CPS == 1 ? 0 : (who == 0 ? 0 : half);
-            const int jhi = CPS == 1 ? 1 : (who == 0 ? half : CPS);
-            int s = 0, buf = 0, item = 0;
+            int s = 0, buf = 0, item = 0, owner = 0;   // owner = item % T.ni
             uint32_t use = 0, duse = 0;
             auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
-                mbar_wait(&full[s_], use_ & 1, T.error_flag, 4);
+                mbar_wait(&full[s_], use_ & 1, T.error_flag, 4, hinted);
+                if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 4);
                 if (PAIR) {   // ... and the peer CTA's half of the stage; its zero flags are not visible here: issue everything
-                    mbar_wait(&peer_full[s_], use_ & 1, T.error_flag, 11);
+                    mbar_wait(&peer_full[s_], use_ & 1, T.error_flag, 11, hinted);
                     tc_fence_after();
                     return dbg_no_mma ? 0u : 0xFu;
                 }
@@ -672,41 +776,50 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
                 return dbg_no_mma ? 0u : m4;
             };
             for (int tl = 0; tl < my_tiles; ++tl) {
-                mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 3);   // the epilogue has drained and zeroed this accumulator
-                if (PAIR) mbar_wait(&peer_dempty[buf], duse & 1, T.error_flag, 12);
+                mbar_wait(&d_empty[buf], duse & 1, T.error_flag, 3, hinted);   // the epilogue has drained and zeroed this accumulator
+                if (PAIR) mbar_wait(&peer_dempty[buf], duse & 1, T.error_flag, 12, hinted);
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
                 const int u = group_id + tl * ngroups;
                 for (int bw = 0; bw < T.bmw; ++bw) {
                   uint32_t sm = stage_bits(unit_word<PAIR>(T, u, bw, gdk), CPS);
                   for (; sm; sm &= sm - 1, ++item) {
-                    const int c_first = 32 * bw + __ffs(sm) - 1;       // first chunk of this non-zero stage
-                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 0);
-                    const uint32_t m_cur = acquire(s, use);
-                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 1);
-                    const int nch = (gdk - c_first < CPS) ? gdk - c_first : CPS;
-                    const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
-                    const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
-                    const bool mine = CPS > 1 || (item & 1) == who;
+                    if (owner == who) {
+                        const int c_first = 32 * bw + __ffs(sm) - 1;       // first chunk of this non-zero stage
+                        if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 0);
+                        const uint32_t m_cur = acquire(s, use);
+                        if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 1);
+                        const int nch = (gdk - c_first < CPS) ? gdk - c_first : CPS;
+                        const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
+                        const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
+                        if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kMaxCps; ++j) {
-                        if (mine && j >= jlo && j < jhi && j < nch && ((m_cur >> j) & 1u)) {
-                            if (elect_one()) {
+                            for (int j = 0; j < kMaxCps; ++j) {
+                                if (j < nch && ((m_cur >> j) & 1u)) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                    if (PAIR) mma_i8_ts_pair(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
-                                    else mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                                        if (PAIR) mma_i8_ts_pair(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        else mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                    }
                                 }
                             }
+                            // arrives when these MMAs have finished reading A (TMEM) and B (smem); pair: in both CTAs
+                            if (PAIR) tc_commit_pair(&empty[s]);
+                            else tc_commit(&empty[s]);
                         }
+                        __syncwarp();
+                        if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 3);
+                    } else {
+                        // not this issuer's item: observe its phase and add this issuer's (in-order) commit
+                        mbar_wait(&full[s], use & 1, T.error_flag, 13, hinted);
+                        if (elect_one()) {
+                            if (PAIR) tc_commit_pair(&empty[s]);
+                            else tc_commit(&empty[s]);
+                        }
+                        __syncwarp();
                     }
-                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 2);
-                    if (elect_one()) {   // arrives when this issuer's MMAs have finished reading A (TMEM) and B (smem); pair: in both CTAs
-                        if (PAIR) tc_commit_pair(&empty[s]);
-                        else tc_commit(&empty[s]);
-                    }
-                    if (lane == 0 && who == 0) QGTC_TRACE(1, item, 3);
+                    if (++owner == T.ni) owner = 0;
                     if (++s == S) { s = 0; ++use; }
                   }
                 }
@@ -723,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
         const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
         const int M = P.M, N = P.N, ob = P.out_bit;
         const unsigned keep = (1u << ob) - 1u;
+        const int dshift = scaled ? 7 : 0;   // accumulators of the scaled expansion hold 128 x the sums
         const int wpr = s128(N) * 4;
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
         int buf = 0;
@@ -750,10 +864,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
             const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
             const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
-            mbar_wait<256>(&d_full[buf], duse & 1, T.error_flag, 6);
+            mbar_wait<256>(&d_full[buf], duse & 1, T.error_flag, 6, hinted);
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
-            const bool valid = true;
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
             if (EPI == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out) + (unsigned long long)z * P.out_bstride;
@@ -765,42 +878,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int n = 16 * cb + j;
-                            if (n < N) out[(size_t)m * N + n] = valid ? (float)v[j] : 0.0f;
+                            if (n < N) out[(size_t)m * N + n] = (float)(v[j] >> dshift);
                         }
                     }
                 }
             } else {
                 uint32_t* out = reinterpret_cast<uint32_t*>(P.out) + (unsigned long long)z * P.out_bstride;
-                uint32_t pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const bool row_ok = m < p8(M);
-                for (int cb = 0; cb < NP / 16; ++cb) {
-                    if (((cb >> 1) & 1) != half) continue;
-                    int v[16];
-                    tmem_ld16(d_tmem + 16 * cb, v);
-#pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        uint32_t four = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int n = 16 * cb + 4 * g4 + e;
-                            uint32_t x = (valid && m < M && n < N) ? ((uint32_t)requant(v[4 * g4 + e], ob) & keep) : 0u;
-                            four |= x << (8 * e);
-                        }
-                        const int nib_pos = 28 - 4 * (((16 * cb + 4 * g4) & 31) >> 2);
-#pragma unroll
-                        for (int p = 0; p < 8; ++p)
-                            if (p < ob) pw[p] |= nibble_of_plane(four, p) << nib_pos;
-                    }
-                    if ((cb & 1) || cb == NP / 16 - 1) {   // a 32-column word is complete (or the tile ends on a half word)
-                        const int w = cb >> 1;
-                        if (row_ok) {
-#pragma unroll
-                            for (int p = 0; p < 8; ++p)
-                                if (p < ob) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = pw[p];
-                        }
-#pragma unroll
-                        for (int p = 0; p < 8; ++p) pw[p] = 0;
-                    }
+                const uint32_t rmask = m < M ? 0xffffffffu : 0u;
+                uint32_t* out_row = out + (unsigned long long)m * wpr;
+                switch (ob) {   // the plane loop is unrolled for the common widths (a runtime bound issues all 8 planes predicated)
+                    case 1: epi_bits_tile<1>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
+                    case 2: epi_bits_tile<2>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
+                    case 4: epi_bits_tile<4>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
+                    case 8: epi_bits_tile<8>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
+                    default: epi_bits_tile<0>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
                 }
                 if (row_ok && half == 0) {   // zero pad words of the row (output buffers are not pre-zeroed)
                     for (int w = (NP + 31) / 32; w < wpr; ++w)
@@ -826,9 +918,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const Tc05Args T
     }
 }
 
-unsigned int* g_error_flag = nullptr;  // one device word per process (first device used)
+unsigned int* g_error_flag = nullptr;  // device alias of g_error_flag_host
+unsigned int* g_error_flag_host = nullptr;  // one mapped host word per process: where a watchdog fired (0x80000000 | site)
 unsigned long long* g_trace = nullptr;  // clock64 trace buffer, only with QGTC_TC05_TRACE=1
-constexpr size_t kTraceWords = 3 * (size_t)kTraceItems * 8;
+constexpr size_t kTraceWords = 8 * (size_t)kTraceItems * 8;
 
 }  // namespace
 
@@ -893,6 +986,16 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.units = pair ? T.spg * a.count : T.total_tiles;
     T.epi = epi;
     T.one = 1u;
+    {
+        static const int ni_env = [] { const char* e = getenv("QGTC_TC05_ISSUERS"); return e ? atoi(e) : 0; }();
+        T.ni = (ni_env >= 1 && ni_env <= kMaxIssuers) ? ni_env : 2;
+        if (pair && T.ni < 2) T.ni = 2;   // the peer CTA's first two issuer warps are its relays
+    }
+    {   // the scaled expansion needs 128 x the largest possible sum to fit an int32 (K < 65793 for 8-bit features)
+        static const bool unscaled_env = [] { const char* e = getenv("QGTC_TC05_UNSCALED"); return e && e[0] == '1'; }();
+        const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
+        if (unscaled_env || max_sum * 128.0 >= 2147483648.0) T.g.flags |= 0x100000u;
+    }
     T.bitmap = a.tile_bitmap;
     T.bmw = (a.gdk + 31) / 32;
     if ((long long)((T.total_tiles + kNumSMs - 1) / kNumSMs + 1) * T.nst > (1ll << 30)) return QGTC_ERR_UNSUPPORTED;
@@ -915,10 +1018,12 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     }
 
     cudaError_t e;
-    if (!g_error_flag) {
-        e = cudaMalloc(&g_error_flag, sizeof(unsigned int));
-        if (e != cudaSuccess) return record_cuda_error(e, "cudaMalloc(tc05 error flag)");
-        cudaMemset(g_error_flag, 0, sizeof(unsigned int));
+    if (!g_error_flag) {   // mapped host memory: the watchdog's code survives the trap that follows it
+        e = cudaHostAlloc(reinterpret_cast<void**>(&g_error_flag_host), sizeof(unsigned int), cudaHostAllocMapped);
+        if (e != cudaSuccess) return record_cuda_error(e, "cudaHostAlloc(tc05 error flag)");
+        *g_error_flag_host = 0u;
+        e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_error_flag), g_error_flag_host, 0);
+        if (e != cudaSuccess) return record_cuda_error(e, "cudaHostGetDevicePointer(tc05 error flag)");
     }
     T.error_flag = g_error_flag;
     static const bool want_trace = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
@@ -964,7 +1069,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaFuncSetAttribute(gemm_tc05)");
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(pair ? 2 * groups : groups);
-            cfg.blockDim = dim3(kThreads);
+            cfg.blockDim = dim3((kMmaWarp + T.ni) * 32);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
@@ -979,13 +1084,22 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
             return check_launch("gemm_tc05_kernel");
         };
-        if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, true>);
-        else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, false>);
+        const bool dbg = T.trace != nullptr || (T.g.flags & 0x2F0000u) != 0;
+        if (dbg) {
+            if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, true>);
+            else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, true>);
+        } else {
+            if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, false>);
+            else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false>);
+        }
     }
     e = cudaFreeAsync(img, st);
     if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "cudaFreeAsync(feature image)");
     return rc;
 }
+
+// debugging aid (not part of the public ABI): the watchdog word (0 = no watchdog fired); readable after a trap
+extern "C" unsigned int qgtc_debug_tc05_error_flag() { return g_error_flag_host ? *reinterpret_cast<volatile unsigned int*>(g_error_flag_host) : 0u; }
 
 // debugging aid (not part of the public ABI): copy the last clock64 trace to the host
 extern "C" int qgtc_debug_tc05_trace(unsigned long long* dst, size_t max_words) {

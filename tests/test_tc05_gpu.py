@@ -89,6 +89,24 @@ def test_tc05_batched(capi, coracle):
     assert torch.equal(pair, out)
 
 
+@pytest.mark.parametrize("M,K,N,b,cnt", [(130, 513, 64, 2, 200), (130, 513, 70, 2, 200), (264, 1100, 16, 1, 300), (129, 385, 128, 4, 150)])
+def test_tc05_many_short_ragged_problems(capi, coracle, M, K, N, b, cnt):
+    """Many small problems per launch with ragged tiles (a few rows in the last tile, one chunk in the last
+    stage): the pipeline items alternate between long and very short, which is what exposed an mbarrier
+    phase-skipping race between the MMA issuers (a fault under load, never in a single problem)."""
+    rng = np.random.default_rng(M * 7 + N)
+    a = coracle.val2bit(rand_adj(rng, M, K, 0.3), 1, False, False)
+    x = coracle.val2bit(rand_features(rng, (K, N), b), b, True, False)
+    want = coracle.bitMM2Bit(a, x, M, K, N, 1, b, b).reshape(-1)
+    da, dx = dev_words(a), dev_words(x)
+    for _ in range(3):
+        out = capi.bitMM2Bit_batched(da, dx, cnt, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
+        torch.cuda.synchronize()
+        got = host_u32(out)
+        assert np.array_equal(got[0].reshape(-1), want) and np.array_equal(got[cnt // 2].reshape(-1), want) and np.array_equal(got[-1].reshape(-1), want)
+        assert bool((out == out[0]).all())
+
+
 def test_tc05_unsupported_shapes_are_refused(capi):
     a = torch.zeros((2 * 8, 4), dtype=torch.int32, device="cuda")
     b = torch.zeros((2 * 4, 128), dtype=torch.int32, device="cuda")
