@@ -963,6 +963,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.cps = 256 / T.NP;
     if (T.cps > kMaxCps) T.cps = kMaxCps;
     if (T.cps < 1) T.cps = 1;
+    if (T.cps == 3) T.cps = 2;   // powers of two only: the TMA swizzle and the expanders' chunk addressing assume it
     static const int cps_cap = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
     if (cps_cap && T.cps > cps_cap) T.cps = cps_cap;       // experiment knob: shallower stages, deeper ring
     if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
