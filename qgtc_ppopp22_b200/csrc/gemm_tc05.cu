@@ -37,7 +37,7 @@ constexpr int kEpilogueWarps = 8;
 constexpr int kLoaderWarp = 24;
 constexpr int kALoaderWarp = 25;
 constexpr int kMmaWarp = 26;      // first MMA issuer (also allocates TMEM); issuer i is warp kMmaWarp + i
-constexpr int kMaxIssuers = 4;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
+constexpr int kMaxIssuers = 2;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
 constexpr int kMmaWarp2 = kMmaWarp + 1;
 constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
 constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
@@ -64,6 +64,7 @@ struct Tc05Args {
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
     int bmw;                        // bitmap words per tile = ceil(gdk / 32)
+    int amode;                      // adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
     unsigned int* error_flag;       // device word set by the watchdog
@@ -359,7 +360,7 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves) {
+__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves, int amode) {
     // One block per (problem, K chunk).  Phase 1 stages the chunk's packed words (bit2 planes x NP columns x 4 words)
     // in shared memory as [plane][word][column]; phase 2 has consecutive threads produce consecutive columns, so the
     // 16-byte stores of a warp are one contiguous 512-byte run of the image.
@@ -386,6 +387,10 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
                 const uint32_t w = pk[(size_t)(q * 4 + s) * NP + n];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[j] |= ((w >> (j0 + j)) & 0x01010101u) << q;
+            }
+            if (amode == 2) {   // the expanders leave adjacency bit c at value 2^(c % 4): rows carry the complementary 2^(3 - c % 4)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] <<= (3 - j);
             }
             // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
             const int h = n / nh, nl = n - h * nh;
@@ -453,7 +458,7 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
 
 // DBG = true adds the clock64 trace and the timing-experiment knobs (flag bits 0x10000..0x200000); the production
 // instance carries none of that code in its (latency-bound) role loops.
-template <int EPI, bool PAIR, bool DBG>
+template <int EPI, bool PAIR, bool DBG, int AMODE>   // AMODE >= 0 fixes the expansion mode at compile time, -1 reads T.amode
 __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
@@ -529,11 +534,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
     const bool dbg_no_st = DBG && (P.flags & 0x10000u) != 0, dbg_no_mma = DBG && (P.flags & 0x20000u) != 0;
     const bool dbg_no_bulk = DBG && (P.flags & 0x40000u) != 0, dbg_no_ldg = DBG && (P.flags & 0x80000u) != 0;
-    // Scaled expansion (default): adjacency bit c of every byte is moved to the byte's MSB by an integer multiply
-    // (FMA pipe) and one AND (ALU pipe), so the A operand holds 0x80 instead of 1 and the accumulators hold
-    // 128 x the true sums; the epilogue shifts them back (exact).  The launcher clears this when
-    // K * (2^bit2 - 1) * 128 could reach 2^31; then bits are moved to bit 0 by a shift + AND (both ALU pipe).
-    const bool scaled = (P.flags & 0x100000u) == 0;
+    // Adjacency expansion modes (T.amode, chosen by the launcher so that no scaled sum can reach 2^31):
+    //  2: bit c of every byte stays where it is within its nibble -- one AND per register (plus one shift per
+    //     word for the upper nibble) -- so the A operand holds 2^(c % 4); prep_b_kernel scales the feature rows by
+    //     2^(3 - c % 4) (needs bit2 <= 5) and the accumulators hold 8 x the sums;
+    //  1: bit c is moved to the byte's MSB by an integer multiply (FMA pipe) and one AND: A holds 0x80, 128 x sums;
+    //  0: bit c is moved to bit 0 by a shift and an AND (both ALU pipe): exact sums.
+    // The epilogue shifts the accumulators back (exact: every term carries the factor).
+    const int amode = AMODE >= 0 ? AMODE : T.amode;
     const bool hinted = !DBG || (P.flags & 0x200000u) == 0;      // knob set: mbarrier waits poll with nanosleep back-off instead of a suspend hint
 
     if (warp < kProducerWarps) {
@@ -572,30 +580,37 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         const bool tr = DBG && (trole >= 0 && lane == 0);
         const bool two = WCH > 1;
         volatile unsigned char* my_flags = flags + c0 * 4 + q;
-        auto expand = [&](const uint4& pv, uint32_t (&r)[32]) -> bool {
-            const bool nz = nojump || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
-            if (nz) {
-                const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-                if (scaled) {
+        // expansion of one 128-bit chunk of this lane's row into the 32 TMEM columns' registers
+        auto expand = [&](const uint4& pv, uint32_t (&r)[32]) {
+            const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+            if (amode == 2) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t hi = w[ks] >> 4;
 #pragma unroll
-                        for (int cidx = 0; cidx < 7; ++cidx) r[ks * 8 + cidx] = (w[ks] * mult[cidx]) & 0x80808080u;
-                        r[ks * 8 + 7] = w[ks] & 0x80808080u;
+                    for (int cidx = 0; cidx < 4; ++cidx) {
+                        r[ks * 8 + cidx] = w[ks] & (0x01010101u << cidx);
+                        r[ks * 8 + 4 + cidx] = hi & (0x01010101u << cidx);
                     }
-                } else {
+                }
+            } else if (amode == 1) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        r[ks * 8] = w[ks] & 0x01010101u;
+                for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                        for (int cidx = 1; cidx < 8; ++cidx) r[ks * 8 + cidx] = (w[ks] >> cidx) & 0x01010101u;
-                    }
+                    for (int cidx = 0; cidx < 7; ++cidx) r[ks * 8 + cidx] = (w[ks] * mult[cidx]) & 0x80808080u;
+                    r[ks * 8 + 7] = w[ks] & 0x80808080u;
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) r[e] = 0u;
+                for (int ks = 0; ks < 4; ++ks) {
+                    r[ks * 8] = w[ks] & 0x01010101u;
+#pragma unroll
+                    for (int cidx = 1; cidx < 8; ++cidx) r[ks * 8 + cidx] = (w[ks] >> cidx) & 0x01010101u;
+                }
             }
-            return nz;
+        };
+        auto is_nonzero = [&](const uint4& pv) -> bool {
+            return nojump || PAIR || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
         };
         for (int k = 0; k < my_items; ++k) {
             if (tr) QGTC_TRACE(trole, k, 0);
@@ -606,12 +621,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             v[1] = two ? *reinterpret_cast<const uint4*>(src + off[1]) : make_uint4(0u, 0u, 0u, 0u);
             if (tr) QGTC_TRACE(trole, k, 1);
             // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
-            // stage's previous use drain, so only the tcgen05.st sits behind the wait
+            // stage's previous use drain, so only the tcgen05.st sits behind the wait.  An all-zero 32 x 128 block is
+            // expanded like any other (to zeros); it only clears its flag so that the MMA can be skipped when the
+            // other three lane quarters are zero too.
             unsigned nzmask = 0;
             const uint32_t st_s = st_addr + (uint32_t)(s * stage_cols);
             {
                 uint32_t r[32];
-                if (expand(v[0], r)) nzmask |= 1u;
+                if (is_nonzero(v[0])) nzmask |= 1u;
+                expand(v[0], r);
                 if (tr) QGTC_TRACE(trole, k, 2);
                 mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
                 tc_fence_after();
@@ -621,7 +639,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             }
             if (two) {   // warp-uniform
                 uint32_t r[32];
-                if (expand(v[1], r)) nzmask |= 2u;
+                if (is_nonzero(v[1])) nzmask |= 2u;
+                expand(v[1], r);
                 if (!dbg_no_st) tmem_st32(st_s + 32u, r);
                 else if (r[5] == 0xdeadbeefu) flags[255] = 1;
             }
@@ -836,7 +855,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
         const int M = P.M, N = P.N, ob = P.out_bit;
         const unsigned keep = (1u << ob) - 1u;
-        const int dshift = scaled ? 7 : 0;   // accumulators of the scaled expansion hold 128 x the sums
+        const int dshift = amode == 1 ? 7 : (amode == 2 ? 3 : 0);   // the accumulators hold 2^dshift x the sums
         const int wpr = s128(N) * 4;
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
         int buf = 0;
@@ -992,10 +1011,12 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         T.ni = (ni_env >= 1 && ni_env <= kMaxIssuers) ? ni_env : 2;
         if (pair && T.ni < 2) T.ni = 2;   // the peer CTA's first two issuer warps are its relays
     }
-    {   // the scaled expansion needs 128 x the largest possible sum to fit an int32 (K < 65793 for 8-bit features)
-        static const bool unscaled_env = [] { const char* e = getenv("QGTC_TC05_UNSCALED"); return e && e[0] == '1'; }();
+    {   // expansion mode: the scaled sums must fit an int32 (mode 1: K < 65793 for 8-bit features)
+        static const int amode_env = [] { const char* e = getenv("QGTC_TC05_AMODE"); return e ? atoi(e) : -1; }();
         const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
-        if (unscaled_env || max_sum * 128.0 >= 2147483648.0) T.g.flags |= 0x100000u;
+        const bool ok2 = a.bit2 <= 5 && max_sum * 8.0 < 2147483648.0, ok1 = max_sum * 128.0 < 2147483648.0;
+        T.amode = ok2 ? 2 : (ok1 ? 1 : 0);
+        if (amode_env == 0 || (amode_env == 1 && ok1) || (amode_env == 2 && ok2)) T.amode = amode_env;   // experiment knob
     }
     T.bitmap = a.tile_bitmap;
     T.bmw = (a.gdk + 31) / 32;
@@ -1058,7 +1079,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     pa.count = img_problems;
     long long pgrid = (long long)a.gdk * img_problems;
     if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * 4 * T.NP * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1);
+    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * 4 * T.NP * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1, T.amode);
     note_launch();
     int rc = check_launch("prep_b_kernel");
 
@@ -1086,12 +1107,18 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             return check_launch("gemm_tc05_kernel");
         };
         const bool dbg = T.trace != nullptr || (T.g.flags & 0x2F0000u) != 0;
+        const bool fl = epi == kEpiFloat;
         if (dbg) {
-            if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, true>);
-            else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false, true>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, true>);
+            if (pair) rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, true, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, true, -1>);
+            else rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, true, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, true, -1>);
+        } else if (pair) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, false, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, false, -1>);
+        } else if (T.amode == 2) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 2>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 2>);
+        } else if (T.amode == 1) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 1>);
         } else {
-            if (pair) rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, true, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, false>);
-            else rc = (epi == kEpiFloat) ? launch(gemm_tc05_kernel<kEpiFloat, false, false>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false>);
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 0>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 0>);
         }
     }
     e = cudaFreeAsync(img, st);
