@@ -40,7 +40,7 @@ constexpr int kMmaWarp = 26;      // first MMA issuer (also allocates TMEM); iss
 constexpr int kMaxIssuers = 2;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
 constexpr int kMmaWarp2 = kMmaWarp + 1;
 constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
-constexpr int kRawSlots = 4;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
+constexpr int kRawSlots = 8;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
 constexpr int kMaxStages = 4;
 constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
 constexpr int kTmemCols = 512;
@@ -53,8 +53,8 @@ struct Tc05Args {
     int stages;                     // A (TMEM) / B (smem) ring depth
     int cps;                        // K chunks per stage (1, 2 or 4)
     int nst;                        // stages per tile = ceil(gdk / cps)
-    int wch;                        // chunks each expander warp handles per item (2 when cps == 4, else 1)
-    int wpi;                        // expander warps per item = 4 * cps / wch; the 16 warps form 16 / wpi groups
+    int wch;                        // chunks each expander warp handles per item (= cps)
+    int wpi;                        // expander warps per item (4: one per TMEM lane quarter); the 16 warps form 16 / wpi groups
     int dbufs;                      // accumulator buffers (1 or 2)
     int mtiles;                     // 128-row tiles per problem
     int total_tiles;                // count * mtiles
@@ -549,23 +549,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // warp = (TMEM lane quarter q, slot t).  An item (stage) is expanded by wpi warps, each taking
         // wch chunks; the 16 warps form G = 16 / wpi groups that take the items round-robin, so a warp
         // has G item periods to get through its (latency-bound) wait / expand / store / signal chain.
-        const int q = warp & 3, t = warp >> 2;
+        const int q = warp & 3, g = warp >> 2;
+        // Each warp expands all chunks of its item for its 32 rows (wpi = 4 warps per item: the fixed cost of an
+        // item -- two waits, two arrivals, addresses -- is paid once per 32 rows x stage), so the groups of four
+        // warps take the items round-robin and a warp has G item periods for its wait / expand / store / signal chain.
         // G <= S is required: a warp that reaches item X has seen the MMAs of item X-G-S complete (it waited for
-        // them at item X-G), which only implies that item X-2S is done -- no mbarrier phase aliasing -- if G <= S.
-        const int WCH = T.wch, spi = T.wpi >> 2;
+        // them at item X-G), which only implies that item X-2S is done -- no mbarrier phase aliasing -- if G <= S
+        // (MMA completion is in item order, see the issuers).  With three stages the fourth group idles.
+        const int WCH = T.wch;
         const int G = min(min(kProducerWarps / T.wpi, S), kRawSlots);
-        const int g = t / spi, c0 = (t - g * spi) * WCH;
         const int row = 32 * q + lane;             // row of the tile == TMEM lane
         const int my_items = g < G ? (n_items - g + G - 1) / G : 0;   // warps beyond the last group idle
-        // byte offsets of this warp's 16-byte chunks of the row inside a raw slot, with the TMA swizzle
-        // (Swizzle<log2(cps),4,3>: address bits [4,4+log2 cps) ^= bits [7,7+log2 cps))
-        uint32_t off[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            uint32_t o = (uint32_t)(row * 16 * CPS + 16 * (c0 + j));
-            o ^= ((o >> 7) & (uint32_t)(CPS - 1)) << 4;
-            off[j] = o;
-        }
+        // byte offset of chunk j of this row inside a raw slot = row_off + ((j ^ swz) << 4): the TMA swizzle
+        // (Swizzle<log2(cps),4,3>) XORs address bits [4,4+log2 cps) with bits [7,7+log2 cps)
+        const uint32_t row_off = (uint32_t)(row * 16 * CPS);
+        const uint32_t swz = (row_off >> 7) & (uint32_t)(CPS - 1);
         // multipliers 2^(7-c) of the scaled expansion; derived from a kernel argument so that ptxas keeps them
         // as IMAD operands (FMA pipe) instead of folding them back into ALU-pipe shifts
         uint32_t mult[8];
@@ -574,12 +572,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 
         int slot = g % kRawSlots, s = g % S;       // raw ring slot and TMEM/B stage of the current item
         uint32_t raw_use = (uint32_t)(g / kRawSlots), use = (uint32_t)(g / S);
-        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + c0 * 32);
+        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)dcols;
         // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
         const int trole = warp == 0 ? 0 : (warp == 1 ? 3 : (warp == 3 ? 4 : (warp == 8 ? 6 : -1)));
         const bool tr = DBG && (trole >= 0 && lane == 0);
-        const bool two = WCH > 1;
-        volatile unsigned char* my_flags = flags + c0 * 4 + q;
+        volatile unsigned char* my_flags = flags + q;
         // expansion of one 128-bit chunk of this lane's row into the 32 TMEM columns' registers
         auto expand = [&](const uint4& pv, uint32_t (&r)[32]) {
             const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -615,10 +612,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         for (int k = 0; k < my_items; ++k) {
             if (tr) QGTC_TRACE(trole, k, 0);
             if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7, hinted);
-            uint4 v[2];
-            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes;
-            v[0] = *reinterpret_cast<const uint4*>(src + off[0]);
-            v[1] = two ? *reinterpret_cast<const uint4*>(src + off[1]) : make_uint4(0u, 0u, 0u, 0u);
+            uint4 v[kMaxCps];
+            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes + row_off;
+#pragma unroll
+            for (int j = 0; j < kMaxCps; ++j)
+                v[j] = j < WCH ? *reinterpret_cast<const uint4*>(src + (((uint32_t)j ^ swz) << 4)) : make_uint4(0u, 0u, 0u, 0u);
             if (tr) QGTC_TRACE(trole, k, 1);
             // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
             // stage's previous use drain, so only the tcgen05.st sits behind the wait.  An all-zero 32 x 128 block is
@@ -637,25 +635,25 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 if (!dbg_no_st) tmem_st32(st_s, r);
                 else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
             }
-            if (two) {   // warp-uniform
-                uint32_t r[32];
-                if (is_nonzero(v[1])) nzmask |= 2u;
-                expand(v[1], r);
-                if (!dbg_no_st) tmem_st32(st_s + 32u, r);
-                else if (r[5] == 0xdeadbeefu) flags[255] = 1;
+#pragma unroll
+            for (int j = 1; j < kMaxCps; ++j) {
+                if (j < WCH) {   // warp-uniform
+                    uint32_t r[32];
+                    if (is_nonzero(v[j])) nzmask |= 1u << j;
+                    expand(v[j], r);
+                    if (!dbg_no_st) tmem_st32(st_s + (uint32_t)(32 * j), r);
+                    else if (r[5] == 0xdeadbeefu) flags[255] = 1;
+                }
             }
             // every lane holds its raw words by now (the votes of the expansions needed them): the slot can be refilled
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[slot]);
+            if (lane < WCH) my_flags[s * 16 + lane * 4] = (unsigned char)((nzmask >> lane) & 1u);
             if (tr) QGTC_TRACE(trole, k, 4);
             if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
             if (tr) QGTC_TRACE(trole, k, 5);
-            if (lane == 0) {
-                my_flags[s * 16] = (unsigned char)(nzmask & 1u);
-                if (two) my_flags[s * 16 + 4] = (unsigned char)((nzmask >> 1) & 1u);
-            }
-            __syncwarp();   // every lane's tcgen05.st has completed
+            __syncwarp();   // every lane's tcgen05.st has completed, the flags are written
             if (lane == 0) mbar_arrive(&full[s]);
             if (tr) QGTC_TRACE(trole, k, 6);
             slot += G;
@@ -987,8 +985,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     if (cps_cap && T.cps > cps_cap) T.cps = cps_cap;       // experiment knob: shallower stages, deeper ring
     if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
     T.nst = (a.gdk + T.cps - 1) / T.cps;
-    T.wch = T.cps == 4 ? 2 : 1;
-    T.wpi = 4 * T.cps / T.wch;
+    T.wch = T.cps;   // one expander warp per lane quarter takes all chunks of an item
+    T.wpi = 4;
     T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
     int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
