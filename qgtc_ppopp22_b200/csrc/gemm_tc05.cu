@@ -404,54 +404,102 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
 // ---------------------------------------------------------------------------------------------
 // The GEMM kernel
 // ---------------------------------------------------------------------------------------------
+// 8 x 8 bit-matrix transpose (Hacker's Delight 7-3) of eight bytes: x = rows 0..3 (row 0 in the top byte),
+// y = rows 4..7.  Afterwards byte (p - 4) of x (p >= 4) / byte p of y (p < 4), counted from the low end, holds
+// bit p of the eight rows with row 0 in its MSB -- the MSB-first order of the packed plane words.
+__device__ __forceinline__ void transpose8x8(uint32_t& x, uint32_t& y) {
+    uint32_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AAu;  x = x ^ t ^ (t << 7);
+    t = (y ^ (y >> 7)) & 0x00AA00AAu;  y = y ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCCu; x = x ^ t ^ (t << 14);
+    t = (y ^ (y >> 14)) & 0x0000CCCCu; y = y ^ t ^ (t << 14);
+    t = (x & 0xF0F0F0F0u) | ((y >> 4) & 0x0F0F0F0Fu);
+    y = ((x << 4) & 0xF0F0F0F0u) | (y & 0x0F0F0F0Fu);
+    x = t;
+}
+
+// Requantize of QGTC_layer_hidden (reference kernel.h:31-37) followed by the "keep bits 0..ob-1" of the packing.
+// NN: the accumulator is known to be non-negative (scaled expansion modes: no int32 wrap possible).
+template <bool NN>
+__device__ __forceinline__ uint32_t requant_keep(int acc, int mx, unsigned keep) {
+    const int rq = NN ? (acc > mx ? mx - 1 : acc) : (acc > mx ? mx - 1 : (acc < 0 ? 1 : acc));
+    return (uint32_t)rq & keep;
+}
+
 // Requantize + plane-pack epilogue of one accumulator tile for one warp (bitMM2Bit): the warp owns TMEM lane
 // quarter q (one row per lane) and every other 32-column word.  OB > 0 fixes the number of output planes at
-// compile time; OB == 0 takes it from `ob_rt`.
-template <int OB>
+// compile time; OB == 0 takes it from `ob_rt`.  Four or more planes are packed through 8 x 8 bit transposes
+// (22 operations per eight values for all planes) instead of one multiply-gather per plane and four values.
+template <int OB, bool NN>
 __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half, int N, int ob_rt, int dshift, uint32_t rmask, bool row_ok,
                                               uint32_t* out_row, unsigned long long opt_offset) {
     constexpr int kPlanes = OB > 0 ? OB : 8;
     const int ob = OB > 0 ? OB : ob_rt;
     const unsigned keep = (1u << ob) - 1u;
     const int mx = 1 << ob;
-    uint32_t pw[kPlanes];
+    for (int w = half; w * 32 < NP; w += 2) {
+        const bool two = w * 32 + 32 <= NP;          // the tile may end on a 16-column half word
+        if (OB >= 4 && two && w * 32 + 32 <= N) {
+            // ---- whole 32-column word: transpose path
+            int v0[16], v1[16];
+            tmem_ld16(d_tmem + 32 * w, v0);
+            tmem_ld16(d_tmem + 32 * w + 16, v1);
+            uint32_t xs[4], ys[4];
 #pragma unroll
-    for (int p = 0; p < kPlanes; ++p) pw[p] = 0u;
-    for (int cb = 0; cb < NP / 16; ++cb) {
-        if (((cb >> 1) & 1) != half) continue;
-        int v[16];
-        tmem_ld16(d_tmem + 16 * cb, v);
-        // rows past M and columns past N contribute zero bits: one byte mask per four values
-        const bool whole = 16 * cb + 16 <= N;
+            for (int g = 0; g < 4; ++g) {
+                uint32_t x = 0, y = 0;
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-            uint32_t four = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int acc = v[4 * g4 + e] >> dshift;
-                const int rq = acc > mx ? mx - 1 : (acc < 0 ? 1 : acc);   // reference kernel.h:31-37
-                four |= ((uint32_t)rq & keep) << (8 * e);
+                for (int e = 0; e < 4; ++e) {
+                    const int a0 = (g < 2 ? v0[8 * g + e] : v1[8 * (g - 2) + e]) >> dshift;
+                    const int a1 = (g < 2 ? v0[8 * g + 4 + e] : v1[8 * (g - 2) + 4 + e]) >> dshift;
+                    x |= requant_keep<NN>(a0, mx, keep) << (24 - 8 * e);
+                    y |= requant_keep<NN>(a1, mx, keep) << (24 - 8 * e);
+                }
+                transpose8x8(x, y);
+                xs[g] = x;
+                ys[g] = y;
             }
-            uint32_t mask = rmask;
-            if (!whole) {
-                const int nv = N - (16 * cb + 4 * g4);   // valid columns of this group of four
-                mask = nv >= 4 ? rmask : (nv <= 0 ? 0u : (rmask & ((1u << (8 * nv)) - 1u)));
-            }
-            four &= mask;
-            const int nib_pos = 28 - 4 * (((16 * cb + 4 * g4) & 31) >> 2);
-#pragma unroll
-            for (int p = 0; p < kPlanes; ++p)
-                if (p < ob) pw[p] |= nibble_of_plane(four, p) << nib_pos;
-        }
-        if ((cb & 1) || cb == NP / 16 - 1) {   // a 32-column word is complete (or the tile ends on a half word)
-            const int w = cb >> 1;
             if (row_ok) {
 #pragma unroll
-                for (int p = 0; p < kPlanes; ++p)
-                    if (p < ob) out_row[(unsigned long long)p * opt_offset + w] = pw[p];
+                for (int p = 0; p < kPlanes; ++p) {
+                    const uint32_t sel = (uint32_t)((p & 3) | ((4 + (p & 3)) << 4));
+                    const uint32_t lo = p >= 4 ? __byte_perm(xs[3], xs[2], sel) : __byte_perm(ys[3], ys[2], sel);
+                    const uint32_t hi = p >= 4 ? __byte_perm(xs[1], xs[0], sel) : __byte_perm(ys[1], ys[0], sel);
+                    out_row[(unsigned long long)p * opt_offset + w] = __byte_perm(lo, hi, 0x5410u) & rmask;
+                }
             }
+            continue;
+        }
+        // ---- general path (few planes, or a word cut by N or by the tile): multiply-gather per plane
+        uint32_t pw[kPlanes];
 #pragma unroll
-            for (int p = 0; p < kPlanes; ++p) pw[p] = 0u;
+        for (int p = 0; p < kPlanes; ++p) pw[p] = 0u;
+        for (int hcb = 0; hcb < (two ? 2 : 1); ++hcb) {
+            const int cb = 2 * w + hcb;
+            int v[16];
+            tmem_ld16(d_tmem + 16 * cb, v);
+            const bool whole = 16 * cb + 16 <= N;   // else: one byte mask per four values
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                uint32_t four = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) four |= requant_keep<NN>(v[4 * g4 + e] >> dshift, mx, keep) << (8 * e);
+                uint32_t mask = rmask;
+                if (!whole) {
+                    const int nv = N - (16 * cb + 4 * g4);   // valid columns of this group of four
+                    mask = nv >= 4 ? rmask : (nv <= 0 ? 0u : (rmask & ((1u << (8 * nv)) - 1u)));
+                }
+                four &= mask;
+                const int nib_pos = 28 - 4 * (4 * hcb + g4);
+#pragma unroll
+                for (int p = 0; p < kPlanes; ++p)
+                    if (p < ob) pw[p] |= nibble_of_plane(four, p) << nib_pos;
+            }
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int p = 0; p < kPlanes; ++p)
+                if (p < ob) out_row[(unsigned long long)p * opt_offset + w] = pw[p];
         }
     }
 }
@@ -904,13 +952,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 const bool row_ok = m < p8(M);
                 const uint32_t rmask = m < M ? 0xffffffffu : 0u;
                 uint32_t* out_row = out + (unsigned long long)m * wpr;
-                switch (ob) {   // the plane loop is unrolled for the common widths (a runtime bound issues all 8 planes predicated)
-                    case 1: epi_bits_tile<1>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
-                    case 2: epi_bits_tile<2>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
-                    case 4: epi_bits_tile<4>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
-                    case 8: epi_bits_tile<8>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
-                    default: epi_bits_tile<0>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset); break;
+                // the plane loop is unrolled for the common widths (a runtime bound issues all 8 planes predicated)
+#define QGTC_EPI_CASE(OBV, NNV) epi_bits_tile<OBV, NNV>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
+                if (dshift > 0) {   // scaled expansion: sums cannot wrap, accumulators are non-negative
+                    switch (ob) {
+                        case 1: QGTC_EPI_CASE(1, true); break;
+                        case 2: QGTC_EPI_CASE(2, true); break;
+                        case 4: QGTC_EPI_CASE(4, true); break;
+                        case 8: QGTC_EPI_CASE(8, true); break;
+                        default: QGTC_EPI_CASE(0, true); break;
+                    }
+                } else {
+                    QGTC_EPI_CASE(0, false);
                 }
+#undef QGTC_EPI_CASE
                 if (row_ok && half == 0) {   // zero pad words of the row (output buffers are not pre-zeroed)
                     for (int w = (NP + 31) / 32; w < wpr; ++w)
                         for (int p = 0; p < ob; ++p) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = 0u;
