@@ -360,31 +360,38 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves, int amode) {
-    // One block per (problem, K chunk).  Phase 1 stages the chunk's packed words (bit2 planes x NP columns x 4 words)
-    // in shared memory as [plane][word][column]; phase 2 has consecutive threads produce consecutive columns, so the
-    // 16-byte stores of a warp are one contiguous 512-byte run of the image.
-    extern __shared__ uint32_t pk[];   // [bit2][4][NP]
-    const int gdk = P.gdk, n_lim = p8(P.N), bit2 = P.bit2;
+__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves, int amode, int CH) {
+    // One block per (problem, group of CH consecutive K chunks).  Phase 1 stages the group's packed words
+    // (bit2 planes x NP columns x CH x 4 words) in shared memory as [plane][chunk][word][column (+1 pad)]: the CH
+    // threads of a column read CH x 16 contiguous bytes of its packed run.  Phase 2 has consecutive threads produce
+    // consecutive columns, so the 16-byte stores of a warp are one contiguous 512-byte run of the image.
+    extern __shared__ uint32_t pk[];   // [bit2][CH][4][NP + 1]
+    // the GEMM grid (launched with programmatic stream serialization) may be scheduled as this grid's blocks retire;
+    // its feature-image loader still waits for this whole grid (griddepcontrol.wait) before the first copy
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const int gdk = P.gdk, n_lim = p8(P.N), bit2 = P.bit2, ld = NP + 1;
     const unsigned long long gdk4 = (unsigned long long)gdk * 4;
     const int nh = NP / halves;
-    for (long long blk = blockIdx.x; blk < (long long)P.count * gdk; blk += gridDim.x) {
-        const int z = (int)(blk / gdk), c = (int)(blk - (long long)z * gdk);
+    const int groups = (gdk + CH - 1) / CH;
+    for (long long blk = blockIdx.x; blk < (long long)P.count * groups; blk += gridDim.x) {
+        const int z = (int)(blk / groups), c0 = (int)(blk - (long long)z * groups) * CH;
+        const int nch = min(CH, gdk - c0);
         const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
-        for (int i = threadIdx.x; i < bit2 * NP; i += blockDim.x) {
-            const int q = i / NP, n = i - q * NP;
+        for (int i = threadIdx.x; i < bit2 * NP * CH; i += blockDim.x) {
+            const int cc = i % CH, t = i / CH, n = t % NP, q = t / NP;
+            if (cc >= nch) continue;
             uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * c);
-            uint32_t* dst = pk + (size_t)q * 4 * NP + n;
-            dst[0] = w.x; dst[NP] = w.y; dst[2 * NP] = w.z; dst[3 * NP] = w.w;
+            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * (c0 + cc));
+            uint32_t* dst = pk + (size_t)((q * CH + cc) * 4) * ld + n;
+            dst[0] = w.x; dst[ld] = w.y; dst[2 * ld] = w.z; dst[3 * ld] = w.w;
         }
         __syncthreads();
-        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c * NP * 128;
-        for (int i = threadIdx.x; i < 8 * NP; i += blockDim.x) {   // item = (k group 0..7, column n), n fastest
-            const int kg = i / NP, n = i - kg * NP, s = kg >> 1, j0 = (kg & 1) * 4;
+        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c0 * NP * 128;
+        for (int i = threadIdx.x; i < nch * 8 * NP; i += blockDim.x) {   // item = (chunk, k group 0..7, column n), n fastest
+            const int n = i % NP, t = i / NP, kg = t & 7, cc = t >> 3, s = kg >> 1, j0 = (kg & 1) * 4;
             uint32_t o[4] = {0u, 0u, 0u, 0u};
             for (int q = 0; q < bit2; ++q) {
-                const uint32_t w = pk[(size_t)(q * 4 + s) * NP + n];
+                const uint32_t w = pk[(size_t)((q * CH + cc) * 4 + s) * ld + n];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) o[j] |= ((w >> (j0 + j)) & 0x01010101u) << q;
             }
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
             }
             // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
             const int h = n / nh, nl = n - h * nh;
-            *reinterpret_cast<uint4*>(base + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
+            *reinterpret_cast<uint4*>(base + (size_t)cc * NP * 128 + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
                 make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
@@ -736,6 +743,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     } else if (warp == kLoaderWarp) {
         // ===================== feature-image loader =====================
         if (lane == 0) {
+            // programmatic dependent launch: everything up to here (and the adjacency pipeline) overlaps the tail
+            // of prep_b_kernel; the image itself is complete and visible only after this wait
+            asm volatile("griddepcontrol.wait;\n" ::: "memory");
             const uint32_t chunk_bytes = (uint32_t)NP * 128u;
             int s = 0;
             uint32_t use = 0;
@@ -1130,9 +1140,13 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
 
     GemmArgs pa = a;
     pa.count = img_problems;
-    long long pgrid = (long long)a.gdk * img_problems;
+    // chunks per block: as many as keep the staging buffer within the default 48 KB of dynamic shared memory
+    int ch = 4;
+    while (ch > 1 && ((size_t)a.bit2 * ch * 4 * (T.NP + 1) * sizeof(uint32_t) > 48 * 1024 || ch > a.gdk)) ch >>= 1;
+    long long pgrid = (long long)((a.gdk + ch - 1) / ch) * img_problems;
     if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * 4 * T.NP * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP, pair ? 2 : 1, T.amode);
+    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * ch * 4 * (T.NP + 1) * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP,
+                                                                                                  pair ? 2 : 1, T.amode, ch);
     note_launch();
     int rc = check_launch("prep_b_kernel");
 
@@ -1147,13 +1161,16 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             cfg.blockDim = dim3((kMmaWarp + T.ni) * 32);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = pair ? 2 : 1;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
+            // start while prep_b_kernel drains (the kernel's image loader does the griddepcontrol.wait)
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = pair ? 1 : 2;
             e2 = cudaLaunchKernelEx(&cfg, kfn, T, tmap);
             note_launch();
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
