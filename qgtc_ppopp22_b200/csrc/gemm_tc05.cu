@@ -22,6 +22,8 @@
 // Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero skips the expansion and
 // reports it; if the whole 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.
 #include <cuda.h>
+#include <utility>
+#include <vector>
 
 #include <cstdlib>
 
@@ -64,6 +66,9 @@ struct Tc05Args {
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
     int bmw;                        // bitmap words per tile = ceil(gdk / 32)
+    unsigned int* conv;             // in-kernel feature conversion: [0] = job ticket, [1 + image] = chunks converted; null: prep_b_kernel ran
+    uint8_t* bimg_w;                // the image, writable (conversion)
+    int conv_images;                // images to convert (1 when every problem aliases one feature matrix)
     int amode;                      // adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
@@ -139,6 +144,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
             __trap();
         }
     }
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -360,48 +370,96 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves, int amode, int CH) {
-    // One block per (problem, group of CH consecutive K chunks).  Phase 1 stages the group's packed words
-    // (bit2 planes x NP columns x CH x 4 words) in shared memory as [plane][chunk][word][column (+1 pad)]: the CH
-    // threads of a column read CH x 16 contiguous bytes of its packed run.  Phase 2 has consecutive threads produce
-    // consecutive columns, so the 16-byte stores of a warp are one contiguous 512-byte run of the image.
-    extern __shared__ uint32_t pk[];   // [bit2][CH][4][NP + 1]
+// One 128-element K chunk c of problem z: packed planes -> the chunk's 128 x NP byte image.  Thread tid of `nthreads`
+// produces the 16-byte items (k group 0..7, column n) with n fastest, so the stores of a warp are one contiguous
+// 512-byte run of the image.  Every item reads its plane words straight from global memory (__ldg, L1-cached: the
+// eight k groups of a column share one 16-byte run of each plane) -- no staging, no barriers, every thread independent.
+__device__ __forceinline__ void convert_chunk(const GemmArgs& P, int z, int c, uint8_t* __restrict__ chunk_img, int NP, int halves, int amode,
+                                              int tid, int nthreads) {
+    const int n_lim = p8(P.N), bit2 = P.bit2;
+    const unsigned long long gdk4 = (unsigned long long)P.gdk * 4;
+    const int nh = NP / halves;
+    const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
+    for (int i = tid; i < 8 * NP; i += nthreads) {
+        const int kg = i / NP, n = i - kg * NP, s = kg >> 1, j0 = (kg & 1) * 4;
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        // byte i of o[j] = value of K element (32 s + 4 (j0 + j) + i) = sum over planes of bit (j0 + j + 8 i) of the
+        // plane's word s, shifted to bit q (+ 3 - j in expansion mode 2: the expanders leave adjacency bit c at
+        // 2^(c % 4), the rows carry the complementary factor).  One shift and one AND-OR per (plane, j).
+        if (n < n_lim) {
+            const unsigned long long idx0 = (unsigned long long)n * gdk4 + 4ull * c + s;
+            for (int q = 0; q < bit2; ++q) {
+                const uint32_t w = ldw(x2, (unsigned long long)q * P.w_offset + idx0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int to = q + (amode == 2 ? 3 - j : 0), from = j0 + j;   // bit `from` of every byte -> bit `to`
+                    const uint32_t sh = to >= from ? (w << (to - from)) : (w >> (from - to));
+                    o[j] |= sh & (0x01010101u << to);
+                }
+            }
+        }
+        // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
+        const int h = n / nh, nl = n - h * nh;
+        *reinterpret_cast<uint4*>(chunk_img + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+constexpr int kPrepChunks = 32;   // K chunks per prep job: 512 contiguous bytes of every (plane, column) run
+
+// BIT2 = number of feature planes, MODE2 = expansion mode 2 (rows scaled by 2^(3 - c % 4)): both fixed at compile time so
+// that every (plane, j) step is one constant shift and one AND-OR
+template <int BIT2, bool MODE2>
+__global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP, int halves) {
+    // One block per (problem, tile of 32 K chunks, block of 8 columns).  Phase 1 stages the job's packed words in
+    // shared memory, [plane][column][chunk x 4 words (+4 pad)]: consecutive threads read consecutive 16-byte pieces of
+    // a column's K run (coalesced 512-byte runs).  Phase 2: thread = (chunk, k group, column), column fastest: the
+    // eight columns of one (chunk, k group) store one contiguous 128-byte row of core matrices.
+    extern __shared__ uint4 pk4[];   // [bit2][8][ld / 4]
     // the GEMM grid (launched with programmatic stream serialization) may be scheduled as this grid's blocks retire;
     // its feature-image loader still waits for this whole grid (griddepcontrol.wait) before the first copy
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    const int gdk = P.gdk, n_lim = p8(P.N), bit2 = P.bit2, ld = NP + 1;
+    constexpr int bit2 = BIT2;
+    const int gdk = P.gdk, n_lim = p8(P.N);
     const unsigned long long gdk4 = (unsigned long long)gdk * 4;
-    const int nh = NP / halves;
-    const int groups = (gdk + CH - 1) / CH;
-    for (long long blk = blockIdx.x; blk < (long long)P.count * groups; blk += gridDim.x) {
-        const int z = (int)(blk / groups), c0 = (int)(blk - (long long)z * groups) * CH;
-        const int nch = min(CH, gdk - c0);
+    const int ktiles = (gdk + kPrepChunks - 1) / kPrepChunks, nblocks = NP / 8, nh = NP / halves;
+    const int ld4 = kPrepChunks + 1;          // uint4 units per (plane, column) row; the pad keeps phase 2 conflict-free
+    const uint32_t* pk = reinterpret_cast<const uint32_t*>(pk4);
+    const long long jobs = (long long)P.count * ktiles * nblocks;
+    for (long long job = blockIdx.x; job < jobs; job += gridDim.x) {
+        const int nb = (int)(job % nblocks);
+        const long long t = job / nblocks;
+        const int kt = (int)(t % ktiles), z = (int)(t / ktiles);
+        const int c_base = kt * kPrepChunks, nch = min(kPrepChunks, gdk - c_base);
         const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
-        for (int i = threadIdx.x; i < bit2 * NP * CH; i += blockDim.x) {
-            const int cc = i % CH, t = i / CH, n = t % NP, q = t / NP;
-            if (cc >= nch) continue;
+        for (int i = threadIdx.x; i < bit2 * 8 * nch; i += blockDim.x) {
+            const int cc = i % nch, r = i / nch, col = r & 7, q = r >> 3, n = nb * 8 + col;
             uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * (c0 + cc));
-            uint32_t* dst = pk + (size_t)((q * CH + cc) * 4) * ld + n;
-            dst[0] = w.x; dst[ld] = w.y; dst[2 * ld] = w.z; dst[3 * ld] = w.w;
+            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * (c_base + cc));
+            pk4[(size_t)(q * 8 + col) * ld4 + cc] = w;
         }
         __syncthreads();
-        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c0 * NP * 128;
-        for (int i = threadIdx.x; i < nch * 8 * NP; i += blockDim.x) {   // item = (chunk, k group 0..7, column n), n fastest
-            const int n = i % NP, t = i / NP, kg = t & 7, cc = t >> 3, s = kg >> 1, j0 = (kg & 1) * 4;
+        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c_base * NP * 128;
+        const int h = (nb * 8) / nh, nbl = nb - h * (nh / 8);        // pair mode keeps the two column halves of a chunk apart
+        for (int i = threadIdx.x; i < nch * 64; i += blockDim.x) {
+            const int col = i & 7, kg = (i >> 3) & 7, cc = i >> 6, s = kg >> 1, j0 = (kg & 1) * 4;
             uint32_t o[4] = {0u, 0u, 0u, 0u};
-            for (int q = 0; q < bit2; ++q) {
-                const uint32_t w = pk[(size_t)((q * CH + cc) * 4 + s) * ld + n];
+            // byte i of o[j] = value of K element (32 s + 4 (j0 + j) + i) = sum over planes of bit (j0 + j + 8 i) of the
+            // plane's word s, moved to bit q (+ 3 - j in expansion mode 2: the expanders leave adjacency bit c at
+            // 2^(c % 4), the rows carry the complementary factor).  After w >>= j0 the source bit is j: one constant
+            // shift and one AND-OR per (plane, j).
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] |= ((w >> (j0 + j)) & 0x01010101u) << q;
-            }
-            if (amode == 2) {   // the expanders leave adjacency bit c at value 2^(c % 4): rows carry the complementary 2^(3 - c % 4)
+            for (int q = 0; q < BIT2; ++q) {
+                const uint32_t w = pk[((size_t)(q * 8 + col) * ld4 + cc) * 4 + s] >> j0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] <<= (3 - j);
+                for (int j = 0; j < 4; ++j) {
+                    const int to = q + (MODE2 ? 3 - j : 0);   // compile-time after unrolling
+                    const uint32_t sh = to >= j ? (w << (to - j)) : (w >> (j - to));
+                    o[j] |= sh & (0x01010101u << to);
+                }
             }
             // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
-            const int h = n / nh, nl = n - h * nh;
-            *reinterpret_cast<uint4*>(base + (size_t)cc * NP * 128 + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
+            *reinterpret_cast<uint4*>(base + (size_t)cc * NP * 128 + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)nbl * 128 + col * 16) =
                 make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncthreads();
@@ -716,6 +774,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             s += G;
             if (s >= S) { s -= S; ++use; }
         }
+        if (!PAIR && T.conv != nullptr && g == G) {
+            // ===================== feature converters (the expander group without items) =====================
+            // The four warps turn packed feature planes into the byte image the MMAs read, one 128-element K
+            // chunk per job, jobs handed out by a global ticket in (image, chunk) order across all CTAs; the
+            // feature loaders wait for "all chunks of my problem's image are done".  Converters wait on nothing
+            // but each other (named barrier 1), so they cannot deadlock the pipeline they feed.
+            volatile int* ticket_slot = reinterpret_cast<volatile int*>(smem_raw + L.misc + 20);
+            const int ctid = (warp - 4 * G) * 32 + lane;
+            const int total_jobs = T.conv_images * gdk;
+            const unsigned long long img_stride = (unsigned long long)gdk * NP * 128;
+            auto csync = [] { asm volatile("bar.sync 1, 128;\n" ::: "memory"); };
+            for (;;) {
+                if (ctid == 0) *ticket_slot = (int)atomicAdd(&T.conv[0], 1u);
+                csync();
+                const int job = *ticket_slot;
+                if (job >= total_jobs) break;
+                const int zi = job / gdk, c = job - zi * gdk;
+                convert_chunk(P, zi, c, T.bimg_w + (unsigned long long)zi * img_stride + (unsigned long long)c * NP * 128, NP, 1, amode, ctid, 128);
+                __threadfence();                                              // this thread's stores, GPU scope ...
+                asm volatile("fence.proxy.async.global;\n" ::: "memory");     // ... and towards the async proxy (bulk copies read them)
+                csync();
+                if (ctid == 0) atomicAdd(&T.conv[1 + zi], 1u);
+            }
+        }
     } else if (warp == kALoaderWarp) {
         // ===================== adjacency TMA loader =====================
         if (lane == 0 && !dbg_no_ldg) {
@@ -747,11 +829,27 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // of prep_b_kernel; the image itself is complete and visible only after this wait
             asm volatile("griddepcontrol.wait;\n" ::: "memory");
             const uint32_t chunk_bytes = (uint32_t)NP * 128u;
-            int s = 0;
+            int s = 0, conv_seen = -1;
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int u = group_id + tl * ngroups;
-                const uint8_t* img = T.bimg + (unsigned long long)unit_geo<PAIR>(T, u, rank).z * T.bimg_gstride;
+                const int z = unit_geo<PAIR>(T, u, rank).z;
+                const uint8_t* img = T.bimg + (unsigned long long)z * T.bimg_gstride;
+                if (!PAIR && T.conv != nullptr) {   // in-kernel conversion: wait until every chunk of this problem's image is written
+                    const int zi = T.bimg_gstride ? z : 0;
+                    if (zi != conv_seen) {
+                        uint32_t spins = 0;
+                        while (ld_acquire_gpu(T.conv + 1 + zi) < (unsigned)gdk) {
+                            __nanosleep(200);
+                            if (++spins > (1u << 24)) {
+                                if (T.error_flag) { atomicExch_system(T.error_flag, 0x80000000u | 15u); __threadfence_system(); }
+                                __trap();
+                            }
+                        }
+                        asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                        conv_seen = zi;
+                    }
+                }
                 for (int w = 0; w < T.bmw; ++w) {
                     uint32_t m = stage_bits(unit_word<PAIR>(T, u, w, gdk), CPS);
                     while (m) {
@@ -1002,6 +1100,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 
 unsigned int* g_error_flag = nullptr;  // device alias of g_error_flag_host
 unsigned int* g_error_flag_host = nullptr;  // one mapped host word per process: where a watchdog fired (0x80000000 | site)
+// kernel timing (qgtc_debug_tc05_time): cudaEvent pairs around the GEMM kernel launches, read by qgtc_debug_tc05_kernel_times
+bool g_time_on = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;
 unsigned long long* g_trace = nullptr;  // clock64 trace buffer, only with QGTC_TC05_TRACE=1
 constexpr size_t kTraceWords = 8 * (size_t)kTraceItems * 8;
 
@@ -1060,6 +1161,12 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     // (cta_group::2, M = 256) and each streams half of the feature image.  Measured on B200 it does not beat the
     // single-CTA form (the adjacency expanders, not the tensor front end or L2, bound the kernel): DESIGN.md 5.4.
     const bool pair = (pair_env || (a.flags & QGTC_FLAG_TC05_PAIR)) && (T.NP % 16 == 0) && ((long long)((p8(a.M) + 127) / 128) * a.count >= 2);
+    // in-kernel feature conversion (opt-in: QGTC_TC05_CONV=1; default is the separate prep_b_kernel): needs an expander
+    // group without items (fewer than four stages).  Measured on B200 (4096 x 4096 x 64,
+    // 96 graphs): the GEMM kernel is bound by its ALU / issue slots, so the converters' instructions cost more inside it
+    // (+17 us at 1 bit, +83 us at 8 bits) than prep_b_kernel and its launch gap cost outside (15 / 29 us).
+    static const bool conv_env = [] { const char* e = getenv("QGTC_TC05_CONV"); return e && e[0] == '1'; }();
+    const bool conv_want = conv_env && !pair;
     while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
@@ -1133,22 +1240,42 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     }
     uint8_t* img = nullptr;
     const int img_problems = b_shared ? 1 : a.count;
-    const size_t img_bytes = (size_t)a.gdk * T.NP * 128 * img_problems;
-    e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes, st);
+    const size_t img_bytes = (((size_t)a.gdk * T.NP * 128 * img_problems) + 255) & ~(size_t)255;
+    const bool conv = conv_want && T.stages < kProducerWarps / T.wpi;    // an idle expander group exists
+    const size_t conv_bytes = conv ? (size_t)(1 + img_problems) * sizeof(unsigned int) : 0;
+    e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes + conv_bytes, st);
     if (e != cudaSuccess) return record_cuda_error(e, "cudaMallocAsync(feature image)");
     T.bimg = img;
+    T.bimg_w = img;
+    T.conv = nullptr;
+    T.conv_images = img_problems;
 
-    GemmArgs pa = a;
-    pa.count = img_problems;
-    // chunks per block: as many as keep the staging buffer within the default 48 KB of dynamic shared memory
-    int ch = 4;
-    while (ch > 1 && ((size_t)a.bit2 * ch * 4 * (T.NP + 1) * sizeof(uint32_t) > 48 * 1024 || ch > a.gdk)) ch >>= 1;
-    long long pgrid = (long long)((a.gdk + ch - 1) / ch) * img_problems;
-    if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
-    prep_b_kernel<<<(int)pgrid, 256, (size_t)a.bit2 * ch * 4 * (T.NP + 1) * sizeof(uint32_t), st>>>(pa, img, (unsigned long long)a.gdk * T.NP * 128, T.NP,
-                                                                                                  pair ? 2 : 1, T.amode, ch);
-    note_launch();
-    int rc = check_launch("prep_b_kernel");
+    int rc = QGTC_OK;
+    if (conv) {   // the GEMM kernel's converter warps build the image: only the job ticket and the per-image counters are prepared here
+        T.conv = reinterpret_cast<unsigned int*>(img + img_bytes);
+        e = cudaMemsetAsync(T.conv, 0, conv_bytes, st);
+        if (e != cudaSuccess) rc = record_cuda_error(e, "cudaMemsetAsync(conversion counters)");
+    } else {
+        GemmArgs pa = a;
+        pa.count = img_problems;
+        long long pgrid = (long long)img_problems * ((a.gdk + kPrepChunks - 1) / kPrepChunks) * (T.NP / 8);
+        if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
+        const size_t psmem = (size_t)a.bit2 * 8 * (kPrepChunks + 1) * sizeof(uint4);    // <= 33 KB
+        const unsigned long long gs = (unsigned long long)a.gdk * T.NP * 128;
+        const int halves = pair ? 2 : 1;
+#define QGTC_PREP(B)                                                                              \
+    case B:                                                                                       \
+        if (T.amode == 2) prep_b_kernel<B, true><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP, halves); \
+        else prep_b_kernel<B, false><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP, halves);  \
+        break;
+        switch (a.bit2) {
+            QGTC_PREP(1) QGTC_PREP(2) QGTC_PREP(3) QGTC_PREP(4) QGTC_PREP(5) QGTC_PREP(6) QGTC_PREP(7) QGTC_PREP(8)
+            default: cudaFreeAsync(img, st); return QGTC_ERR_UNSUPPORTED;
+        }
+#undef QGTC_PREP
+        note_launch();
+        rc = check_launch("prep_b_kernel");
+    }
 
     if (rc == QGTC_OK) {
         const int smem = smem_layout(T.NP, T.stages, T.cps, pair).total + 1024;
@@ -1170,8 +1297,14 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = pair ? 1 : 2;
+            cfg.numAttrs = (pair || conv) ? 1 : 2;
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (g_time_on && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess) cudaEventRecord(ev0, st);
             e2 = cudaLaunchKernelEx(&cfg, kfn, T, tmap);
+            if (ev0 && ev1) {
+                cudaEventRecord(ev1, st);
+                g_time_events.emplace_back(ev0, ev1);
+            }
             note_launch();
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
             return check_launch("gemm_tc05_kernel");
@@ -1198,6 +1331,22 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
 
 // debugging aid (not part of the public ABI): the watchdog word (0 = no watchdog fired); readable after a trap
 extern "C" unsigned int qgtc_debug_tc05_error_flag() { return g_error_flag_host ? *reinterpret_cast<volatile unsigned int*>(g_error_flag_host) : 0u; }
+
+// measurement aid (not part of the public ABI): with timing on, every gemm_tc05_kernel launch is bracketed by a
+// pair of CUDA events on its stream (which also keeps the kernel from overlapping the tail of prep_b_kernel);
+// qgtc_debug_tc05_kernel_times waits for them and returns the kernels' durations in ms, oldest first.
+extern "C" void qgtc_debug_tc05_time(int on) { g_time_on = on != 0; }
+extern "C" int qgtc_debug_tc05_kernel_times(float* dst, int max_n) {
+    int n = 0;
+    for (auto& pr : g_time_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess && n < max_n) dst[n++] = ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_time_events.clear();
+    return n;
+}
 
 // debugging aid (not part of the public ABI): copy the last clock64 trace to the host
 extern "C" int qgtc_debug_tc05_trace(unsigned long long* dst, size_t max_words) {
