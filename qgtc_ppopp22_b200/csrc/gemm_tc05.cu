@@ -2,8 +2,8 @@
 //
 // Data flow of one CTA (persistent, one per SM), for a 128-row adjacency tile:
 //
-//   packed 1-bit adjacency tile  --TMA (cp.async.bulk.tensor, 64B/32B swizzle)--> smem ring
-//        --LDS.128--> registers --(w >> c) & 0x01010101 : 4 bytes per register--> 32 registers
+//   packed 1-bit adjacency tile  --TMA (cp.async.bulk.tensor, 64B/32B swizzle)--> smem ring (8 slots)
+//        --LDS.128--> registers --one AND per register (expansion mode 2)--> 32 registers
 //        = 128 u8 of one row  --tcgen05.st.32x32b.x32--> TMEM (the MMA's A operand, row = lane)
 //   feature "image" (u8, K-major core matrices, produced once per call by prep_b_kernel)
 //        --cp.async.bulk + mbarrier--> smem stage (the MMA's B operand, no-swizzle descriptor)
@@ -12,15 +12,18 @@
 //
 // The adjacency never exists as bytes in shared or global memory: 1 bit per element is read from
 // HBM, the 8x inflation happens in registers and goes straight to tensor memory.  The K order
-// inside a 32-element step is permuted (byte i of column c is bit c+8i of the packed word) so the
-// expansion is one shift and one mask per register; the feature image uses the same permutation.
+// inside a 32-element step is permuted (byte i of column c is bit c+8i of the packed word) so that a
+// register of four A bytes is a mask of the packed word; the feature image uses the same permutation
+// (and, in expansion mode 2, carries the power of two that turns the masked bit back into a 1).
 //
-// A pipeline stage covers `cps` K chunks of 128 bits (cps * NP = 256, so a stage is always 16
+// A pipeline stage ("item") covers `cps` K chunks of 128 bits (cps * NP = 256, so a stage is always 16
 // column-64-equivalent MMAs) to amortise the per-stage barrier round trips.
-// Warp roles: warps 0-15 adjacency expanders (warp = TMEM lane quarter x chunk of the stage),
-// 16-23 epilogue (lane quarter x column half), 24 feature loader, 25/27 MMA issuers, 26 adjacency TMA loader.
-// Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero skips the expansion and
-// reports it; if the whole 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.
+// Warp roles: warps 0-15 adjacency expanders (warp = TMEM lane quarter of one of four groups; a group
+// expands whole items, the groups take the items round-robin), 16-23 epilogue (lane quarter x column half),
+// 24 feature loader, 25 adjacency TMA loader, 26-27 MMA issuers (items round-robin, in-order commits).
+// Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero reports it; if the whole
+// 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.  With a precomputed tile bitmap
+// (qgtc_tile_bitmap) all-zero stages are skipped by every role.
 #include <cuda.h>
 #include <utility>
 #include <vector>
@@ -223,15 +226,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
-// SS form (A from shared memory); only used by a timing experiment
-__device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
@@ -309,23 +303,6 @@ __host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, i
     L.total = L.misc + 32;
     return L;
 }
-
-// Walks a CTA's (tile, chunk) items with a fixed stride, tracking the ring stage and how often it
-// has been used -- all by increments, no divisions in the hot loops.
-struct Cursor {
-    int tl, c, s;
-    uint32_t use;
-    __device__ __forceinline__ void init(int start, int gdk, int S) {
-        tl = 0; c = start; s = start % S; use = 0;
-        while (c >= gdk) { c -= gdk; ++tl; }
-    }
-    __device__ __forceinline__ void advance(int step, int gdk, int S) {   // step <= S
-        c += step;
-        while (c >= gdk) { c -= gdk; ++tl; }
-        s += step;
-        if (s >= S) { s -= S; ++use; }
-    }
-};
 
 // Zero-tile jumping from the precomputed bitmap: a stage (cps chunks) is visited iff one of its chunk bits is set.
 // stage_bits() collapses a word of chunk bits to one bit per stage (at the stage's first chunk position).
@@ -578,7 +555,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const GemmArgs& P = T.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps, nst = T.nst;
+    const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps;
     const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0);
     const int rank = PAIR ? (int)cluster_ctarank() : 0;            // 0 = leader (issues the MMAs)
     const int group_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -1008,7 +985,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // a warp owns the 16-column blocks cb with (cb >> 1) % 2 == half, i.e. every other 32-column word
         const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
         const int M = P.M, N = P.N, ob = P.out_bit;
-        const unsigned keep = (1u << ob) - 1u;
         const int dshift = amode == 1 ? 7 : (amode == 2 ? 3 : 0);   // the accumulators hold 2^dshift x the sums
         const int wpr = s128(N) * 4;
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
@@ -1129,10 +1105,11 @@ bool tc05_supports(const GemmArgs& a, int epi) {
     if (a.bit1 != 1) return false;                 // the expanders handle a single adjacency plane
     if (p8(a.N) > 256) return false;               // one MMA N block
     if (!a_in_bounds(a) || !encode_tiled_fn()) return false;
-    // measured single-call latency (profiles/r1_single_call_sweep.txt): tcgen05 wins from ~0.04 GOP up
-    // (e.g. 2258 x 2258 x 16: 11.7 us vs 20.8 us); below that the two launches and the pipeline prologue cost more
+    // measured single-call latency (profiles/r1_single_call_sweep.txt): tcgen05 wins from the smallest measured
+    // problem up (759 x 759 x 16, 0.018 GOP: 6.2 us vs 8.0 us; 2258 x 2258 x 64: 8.2 us vs 37 us); below that the
+    // two launches and the pipeline prologue are assumed to cost more than the single legacy kernel
     const double ops = 2.0 * a.M * (double)a.K * a.N * a.count;
-    return ops >= 4.0e7;
+    return ops >= 1.5e7;
 }
 
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
