@@ -249,7 +249,9 @@ def run_ours(args):
         per_bit_kernel = dict(per_bit)
     kern_ms = sum(per_bit_kernel.values()) / len(per_bit_kernel)
     peaks = measured_peaks()
-    int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
+    # the kernel is timed alone (events around each launch): the burst figure applies; the sustained one (1404 TF/s
+    # bf16, measured with the SM clock power-capped to ~1.36 GHz) is exceeded by this engine at N = 128
+    int8_peak = 2.0 * peaks["bf16_tflops"]
     achieved = OPS_PER_GEMM * G / (kern_ms * 1e-3) / 1e12
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this command (profiles/)
@@ -326,7 +328,8 @@ def run_ours(args):
                          "frac": round(achieved / int8_peak, 4), "traffic": traffic,
                          "note": "integer ops/s of gemm_tc05_kernel alone (CUDA events around each of its launches, mean over the four bit "
                                  "widths; the call also runs prep_b_kernel: see per_bit_ms_per_call); peak = 2 x %s dense "
-                                 "bf16 (sustained) from MEASURED_PEAKS.json, INT8:bf16 = 2:1 on B200" % peaks["source"]},
+                                 "bf16 (burst, kernel timed alone) from MEASURED_PEAKS.json, INT8:bf16 = 2:1 on B200; nominal "
+                                 "INT8 peak is 4500" % peaks["source"]},
             "cpu_baseline": cpu,
             "cluster_gcn": epoch,
             "clocks": clocks,
