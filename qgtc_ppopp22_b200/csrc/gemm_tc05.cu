@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
             const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
-            mbar_wait<256>(&d_full[buf], duse & 1, T.error_flag, 6, hinted);
+            mbar_wait<512>(&d_full[buf], duse & 1, T.error_flag, 6, false);   // long wait (a whole tile): sleep between polls instead of the hinted try_wait, which wakes at every barrier event of the CTA
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
