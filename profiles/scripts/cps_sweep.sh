@@ -1,0 +1,10 @@
+for c in 4 2 1; do echo "cps=$c"; QGTC_TC05_CPS=$c python - <<'PY'
+import sys, os, json
+sys.path.insert(0, os.path.join(os.getcwd(), "profiles", "scripts"))
+from engine_sweep import run
+from qgtc_ppopp22_b200 import capi
+for N in (64, 16, 128):
+    ms, tops = run(capi.ENGINE_TCGEN05, 4096, 4096, N, 2, 128)
+    print(json.dumps({"N": N, "ms": round(ms, 4), "tops": round(tops, 1)}))
+PY
+done
