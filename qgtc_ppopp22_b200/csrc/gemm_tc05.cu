@@ -468,11 +468,29 @@ __device__ __forceinline__ uint32_t requant_keep(int acc, int mx, unsigned keep)
     return (uint32_t)rq & keep;
 }
 
+// Requantized, masked-to-ob-bits bytes of four accumulators, first one in the low byte.
+// FAST (scaled accumulators = 8 x sum, non-negative, ob <= 4): clamp to 8 (2^ob + 1) so that every value fits a byte,
+// gather the four low bytes with three PRMTs and finish byte-parallel: >> 3; the byte 2^ob + 1 ("above the range")
+// becomes 2^ob - 1, the byte 2^ob becomes 0 (reference kernel.h:31-37,350), everything else passes.
+template <bool NN, bool FAST>
+__device__ __forceinline__ uint32_t requant4(int a0, int a1, int a2, int a3, int dshift, int ob, int mx, unsigned keep) {
+    if (FAST) {
+        const int lim = (mx + 1) << 3;
+        const uint32_t t0 = (uint32_t)min(a0, lim), t1 = (uint32_t)min(a1, lim), t2 = (uint32_t)min(a2, lim), t3 = (uint32_t)min(a3, lim);
+        const uint32_t lo = __byte_perm(t0, t1, 0x1140u), hi = __byte_perm(t2, t3, 0x1140u);   // bytes 1..3 of every t are zero
+        uint32_t four = (__byte_perm(lo, hi, 0x5410u) >> 3) & 0x1F1F1F1Fu;
+        const uint32_t over = (four >> ob) & four & 0x01010101u;                                 // bytes equal to 2^ob + 1
+        return (four & (keep * 0x01010101u)) | (over * keep);
+    }
+    return requant_keep<NN>(a0 >> dshift, mx, keep) | (requant_keep<NN>(a1 >> dshift, mx, keep) << 8) |
+           (requant_keep<NN>(a2 >> dshift, mx, keep) << 16) | (requant_keep<NN>(a3 >> dshift, mx, keep) << 24);
+}
+
 // Requantize + plane-pack epilogue of one accumulator tile for one warp (bitMM2Bit): the warp owns TMEM lane
 // quarter q (one row per lane) and every other 32-column word.  OB > 0 fixes the number of output planes at
 // compile time; OB == 0 takes it from `ob_rt`.  Four or more planes are packed through 8 x 8 bit transposes
 // (22 operations per eight values for all planes) instead of one multiply-gather per plane and four values.
-template <int OB, bool NN>
+template <int OB, bool NN, bool FAST>
 __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half, int N, int ob_rt, int dshift, uint32_t rmask, bool row_ok,
                                               uint32_t* out_row, unsigned long long opt_offset) {
     constexpr int kPlanes = OB > 0 ? OB : 8;
@@ -489,14 +507,10 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             uint32_t xs[4], ys[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                uint32_t x = 0, y = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int a0 = (g < 2 ? v0[8 * g + e] : v1[8 * (g - 2) + e]) >> dshift;
-                    const int a1 = (g < 2 ? v0[8 * g + 4 + e] : v1[8 * (g - 2) + 4 + e]) >> dshift;
-                    x |= requant_keep<NN>(a0, mx, keep) << (24 - 8 * e);
-                    y |= requant_keep<NN>(a1, mx, keep) << (24 - 8 * e);
-                }
+                const int* vv = g < 2 ? &v0[8 * g] : &v1[8 * (g - 2)];
+                // the transpose wants the first column in the top byte: reverse the four bytes
+                uint32_t x = __byte_perm(requant4<NN, FAST>(vv[0], vv[1], vv[2], vv[3], dshift, ob, mx, keep), 0u, 0x0123u);
+                uint32_t y = __byte_perm(requant4<NN, FAST>(vv[4], vv[5], vv[6], vv[7], dshift, ob, mx, keep), 0u, 0x0123u);
                 transpose8x8(x, y);
                 xs[g] = x;
                 ys[g] = y;
@@ -523,9 +537,7 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             const bool whole = 16 * cb + 16 <= N;   // else: one byte mask per four values
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-                uint32_t four = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) four |= requant_keep<NN>(v[4 * g4 + e] >> dshift, mx, keep) << (8 * e);
+                uint32_t four = requant4<NN, FAST>(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3], dshift, ob, mx, keep);
                 uint32_t mask = rmask;
                 if (!whole) {
                     const int nv = N - (16 * cb + 4 * g4);   // valid columns of this group of four
@@ -1037,17 +1049,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 const uint32_t rmask = m < M ? 0xffffffffu : 0u;
                 uint32_t* out_row = out + (unsigned long long)m * wpr;
                 // the plane loop is unrolled for the common widths (a runtime bound issues all 8 planes predicated)
-#define QGTC_EPI_CASE(OBV, NNV) epi_bits_tile<OBV, NNV>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
-                if (dshift > 0) {   // scaled expansion: sums cannot wrap, accumulators are non-negative
+#define QGTC_EPI_CASE(OBV, NNV, FASTV) epi_bits_tile<OBV, NNV, FASTV>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
+                if (dshift == 3 && ob <= 4) {   // expansion mode 2: accumulators = 8 x sums, non-negative; byte-parallel requantize
                     switch (ob) {
-                        case 1: QGTC_EPI_CASE(1, true); break;
-                        case 2: QGTC_EPI_CASE(2, true); break;
-                        case 4: QGTC_EPI_CASE(4, true); break;
-                        case 8: QGTC_EPI_CASE(8, true); break;
-                        default: QGTC_EPI_CASE(0, true); break;
+                        case 1: QGTC_EPI_CASE(1, true, true); break;
+                        case 2: QGTC_EPI_CASE(2, true, true); break;
+                        case 4: QGTC_EPI_CASE(4, true, true); break;
+                        default: QGTC_EPI_CASE(0, true, true); break;
+                    }
+                } else if (dshift > 0) {   // scaled expansion: sums cannot wrap, accumulators are non-negative
+                    switch (ob) {
+                        case 1: QGTC_EPI_CASE(1, true, false); break;
+                        case 2: QGTC_EPI_CASE(2, true, false); break;
+                        case 4: QGTC_EPI_CASE(4, true, false); break;
+                        case 8: QGTC_EPI_CASE(8, true, false); break;
+                        default: QGTC_EPI_CASE(0, true, false); break;
                     }
                 } else {
-                    QGTC_EPI_CASE(0, false);
+                    QGTC_EPI_CASE(0, false, false);
                 }
 #undef QGTC_EPI_CASE
                 if (row_ok && half == 0) {   // zero pad words of the row (output buffers are not pre-zeroed)
