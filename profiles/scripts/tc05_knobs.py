@@ -14,7 +14,7 @@ from qgtc_ppopp22_b200 import capi  # noqa: E402
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from engine_sweep import run  # noqa: E402
 
-KNOBS = {"none": 0, "nanosleep_waits": 0x200000, "nojump": 1, "no_st": 0x10000, "no_mma": 0x20000, "no_bulk": 0x40000, "no_ldg": 0x80000 | 1,
+KNOBS = {"none": 0, "dbg_instance": 0x200000, "alt_accumulators": 0x400000, "nanosleep_waits": 0x200000, "nojump": 1, "no_st": 0x10000, "no_mma": 0x20000, "no_bulk": 0x40000, "no_ldg": 0x80000 | 1,
          "no_st+no_mma": 0x30000, "no_st+no_mma+no_bulk": 0x70000, "all_off": 0xF0000 | 1}
 
 if __name__ == "__main__":

@@ -636,6 +636,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
     const bool dbg_no_st = DBG && (P.flags & 0x10000u) != 0, dbg_no_mma = DBG && (P.flags & 0x20000u) != 0;
     const bool dbg_no_bulk = DBG && (P.flags & 0x40000u) != 0, dbg_no_ldg = DBG && (P.flags & 0x80000u) != 0;
+    const bool dbg_alt_d = DBG && (P.flags & 0x400000u) != 0;   // alternate the MMAs of a tile between both accumulators (is the D dependency the pace?)
     // Adjacency expansion modes (T.amode, chosen by the launcher so that no scaled sum can reach 2^31):
     //  2: bit c of every byte stays where it is within its nibble -- one AND per register (plus one shift per
     //     word for the upper nibble) -- so the A operand holds 2^(c % 4); prep_b_kernel scales the feature rows by
@@ -961,8 +962,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 #pragma unroll
                                     for (int ks = 0; ks < 4; ++ks) {
                                         const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                        if (PAIR) mma_i8_ts_pair(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
-                                        else mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        const uint32_t d_use = (dbg_alt_d && (ks & 1)) ? (d_tmem ^ (uint32_t)NP) : d_tmem;
+                                        if (PAIR) mma_i8_ts_pair(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        else mma_i8_ts(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
                                     }
                                 }
                             }
@@ -1305,7 +1307,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
             return check_launch("gemm_tc05_kernel");
         };
-        const bool dbg = T.trace != nullptr || (T.g.flags & 0x2F0000u) != 0;
+        const bool dbg = T.trace != nullptr || (T.g.flags & 0x6F0000u) != 0;
         const bool fl = epi == kEpiFloat;
         if (dbg) {
             if (pair) rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, true, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, true, -1>);
