@@ -155,3 +155,41 @@ def test_tilemap_batched(capi, coracle):
     assert torch.equal(capi.bitMM2Bit_tilemap(d1, d2, bm, cnt, M, K, N, b, b, engine=capi.ENGINE_TCGEN05, flags=capi.FLAG_TC05_PAIR), out)
     for i in range(cnt):
         assert np.array_equal(host_u32(out[i]).reshape(-1), coracle.bitMM2Bit(x1[i], x2[i], M, K, N, 1, b, b).reshape(-1)), i
+
+
+_MODE_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from qgtc_ppopp22_b200 import capi
+torch.manual_seed(5)
+bad = []
+for (M, K, N, b, ob) in [(300, 1000, 40, 2, 2), (515, 515, 64, 4, 4), (257, 640, 72, 5, 3), (1024, 1024, 64, 1, 1), (130, 513, 16, 3, 8)]:
+    A = (torch.rand(M, K, device="cuda") < 0.2).float()
+    X = torch.randint(0, 1 << b, (K, N), device="cuda").float()
+    a, x, x8 = capi.val2bit(A, 1, False, False), capi.val2bit(X, b, True, False), capi.val2bit(X, b, True, True)
+    for cnt in (1, 5):
+        ref = capi.bitMM2Bit_batched(a, x, cnt, M, K, N, 1, b, ob, engine=capi.ENGINE_MMA_SYNC)
+        out = capi.bitMM2Bit_batched(a, x, cnt, M, K, N, 1, b, ob, engine=capi.ENGINE_TCGEN05)
+        if not torch.equal(out, ref):
+            bad.append(("bits", M, K, N, b, ob, cnt))
+    f0 = capi.bitMM2Int(a, x8, M, K, N, 1, b, False, engine=capi.ENGINE_MMA_SYNC)
+    f1 = capi.bitMM2Int(a, x8, M, K, N, 1, b, False, engine=capi.ENGINE_TCGEN05)
+    if not torch.equal(f0, f1):
+        bad.append(("int", M, K, N, b))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+"""
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tc05_expansion_modes_agree(mode):
+    """The three adjacency expansion modes of the tcgen05 engine (plain shift + AND, x128 multiply + AND, AND-only with
+    pre-scaled feature rows) are chosen by operand range; QGTC_TC05_AMODE (read once per process) forces one where it
+    is exact, so each runs in its own interpreter against the mma.sync engine."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QGTC_TC05_AMODE=str(mode))
+    r = subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
