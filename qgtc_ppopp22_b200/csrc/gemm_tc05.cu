@@ -558,9 +558,10 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
     }
 }
 
-// DBG = true adds the clock64 trace and the timing-experiment knobs (flag bits 0x10000..0x200000); the production
+// DBG = 2 adds the clock64 trace and the timing-experiment knobs (flag bits 0x10000..0x400000), DBG = 1 only the
+// trace (the production code path with seven clock reads per item, for timelines that can be trusted); the production
 // instance carries none of that code in its (latency-bound) role loops.
-template <int EPI, bool PAIR, bool DBG, int AMODE>   // AMODE >= 0 fixes the expansion mode at compile time, -1 reads T.amode
+template <int EPI, bool PAIR, int DBG, int AMODE>   // AMODE >= 0 fixes the expansion mode at compile time, -1 reads T.amode
 __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
@@ -634,9 +635,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     const int n_items = *item_count;      // launch_gemm_tc05 guarantees this fits 31 bits
     const bool nojump = (P.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
     // timing-experiment knobs (results are wrong when set; used only by profiles/scripts/tc05_knobs.py)
-    const bool dbg_no_st = DBG && (P.flags & 0x10000u) != 0, dbg_no_mma = DBG && (P.flags & 0x20000u) != 0;
-    const bool dbg_no_bulk = DBG && (P.flags & 0x40000u) != 0, dbg_no_ldg = DBG && (P.flags & 0x80000u) != 0;
-    const bool dbg_alt_d = DBG && (P.flags & 0x400000u) != 0;   // alternate the MMAs of a tile between both accumulators (is the D dependency the pace?)
+    const bool dbg_no_st = DBG == 2 && (P.flags & 0x10000u) != 0, dbg_no_mma = DBG == 2 && (P.flags & 0x20000u) != 0;
+    const bool dbg_no_bulk = DBG == 2 && (P.flags & 0x40000u) != 0, dbg_no_ldg = DBG == 2 && (P.flags & 0x80000u) != 0;
+    const bool dbg_alt_d = DBG == 2 && (P.flags & 0x400000u) != 0;   // alternate the MMAs of a tile between both accumulators (is the D dependency the pace?)
     // Adjacency expansion modes (T.amode, chosen by the launcher so that no scaled sum can reach 2^31):
     //  2: bit c of every byte stays where it is within its nibble -- one AND per register (plus one shift per
     //     word for the upper nibble) -- so the A operand holds 2^(c % 4); prep_b_kernel scales the feature rows by
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     //  0: bit c is moved to bit 0 by a shift and an AND (both ALU pipe): exact sums.
     // The epilogue shifts the accumulators back (exact: every term carries the factor).
     const int amode = AMODE >= 0 ? AMODE : T.amode;
-    const bool hinted = !DBG || (P.flags & 0x200000u) == 0;      // knob set: mbarrier waits poll with nanosleep back-off instead of a suspend hint
+    const bool hinted = DBG != 2 || (P.flags & 0x200000u) == 0;      // knob set: mbarrier waits poll with nanosleep back-off instead of a suspend hint
 
     if (warp < kProducerWarps) {
         // ===================== adjacency expanders =====================
@@ -1307,19 +1308,23 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             if (e2 != cudaSuccess) return record_cuda_error(e2, "cudaLaunchKernelEx(gemm_tc05)");
             return check_launch("gemm_tc05_kernel");
         };
-        const bool dbg = T.trace != nullptr || (T.g.flags & 0x6F0000u) != 0;
+        const bool knobs = (T.g.flags & 0x6F0000u) != 0, trace = T.trace != nullptr;
         const bool fl = epi == kEpiFloat;
-        if (dbg) {
-            if (pair) rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, true, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, true, -1>);
-            else rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, true, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, true, -1>);
+        if (knobs) {
+            if (pair) rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, 2, -1>);
+            else rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
         } else if (pair) {
-            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, false, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, false, -1>);
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, 0, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, 0, -1>);
+        } else if (trace && !fl && T.amode == 2) {
+            rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2>);       // the production code path + clock reads
+        } else if (trace) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
         } else if (T.amode == 2) {
-            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 2>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 2>);
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 2>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 2>);
         } else if (T.amode == 1) {
-            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 1>);
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 1>);
         } else {
-            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, false, 0>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, false, 0>);
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 0>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 0>);
         }
     }
     e = cudaFreeAsync(img, st);
