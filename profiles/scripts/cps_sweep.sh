@@ -1,4 +1,4 @@
-for c in 4 2 1; do echo "cps=$c"; QGTC_TC05_CPS=$c python - <<'PY'
+for c in 4 3 2 1; do echo "cps=$c"; QGTC_TC05_CPS=$c python - <<'PY'
 import sys, os, json
 sys.path.insert(0, os.path.join(os.getcwd(), "profiles", "scripts"))
 from engine_sweep import run

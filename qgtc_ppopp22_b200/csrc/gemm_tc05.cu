@@ -304,13 +304,6 @@ __host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, i
     return L;
 }
 
-// Zero-tile jumping from the precomputed bitmap: a stage (cps chunks) is visited iff one of its chunk bits is set.
-// stage_bits() collapses a word of chunk bits to one bit per stage (at the stage's first chunk position).
-__device__ __forceinline__ uint32_t stage_bits(uint32_t w, int cps) {
-    if (cps == 2) return (w | (w >> 1)) & 0x55555555u;
-    if (cps == 4) return (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
-    return w;
-}
 // word w of a tile's chunk bits; without a bitmap every existing chunk counts
 __device__ __forceinline__ uint32_t tile_word(const uint32_t* bm_tile, int w, int gdk) {
     const int left = gdk - 32 * w;
@@ -340,6 +333,17 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
     uint32_t r = tile_word(T.bitmap + ((size_t)z * T.mtiles + mt0) * T.bmw, w, gdk);
     if (mt0 + 1 < T.mtiles) r |= tile_word(T.bitmap + ((size_t)z * T.mtiles + mt0 + 1) * T.bmw, w, gdk);
     return r;
+}
+
+// Zero-tile jumping from the precomputed bitmap: stage st (chunks [st * cps, st * cps + cps), any cps) of a unit is
+// visited iff one of its chunk bits is set; without a bitmap every stage is.  Every role walks the stages with this.
+template <bool PAIR>
+__device__ __forceinline__ bool stage_present(const Tc05Args& T, int u, int st, int cps, int gdk) {
+    if (!T.bitmap) return true;
+    const int c = st * cps, w = c >> 5, sh = c & 31;
+    uint32_t bits = unit_word<PAIR>(T, u, w, gdk) >> sh;
+    if (sh + cps > 32 && w + 1 < T.bmw) bits |= unit_word<PAIR>(T, u, w + 1, gdk) << (32 - sh);
+    return (bits & ((1u << cps) - 1u)) != 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -617,9 +621,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     {
         const int units_here = (T.units - group_id + ngroups - 1) / ngroups;
         int cnt = 0;
-        for (int i = threadIdx.x; i < units_here * T.bmw; i += blockDim.x) {
-            const int ul = i / T.bmw, w = i - ul * T.bmw;
-            cnt += __popc(stage_bits(unit_word<PAIR>(T, group_id + ul * ngroups, w, P.gdk), T.cps));
+        for (int i = threadIdx.x; i < units_here * T.nst; i += blockDim.x) {
+            const int ul = i / T.nst, st = i - ul * T.nst;
+            cnt += stage_present<PAIR>(T, group_id + ul * ngroups, st, T.cps, P.gdk) ? 1 : 0;
         }
         if (cnt) atomicAdd(item_count, cnt);
     }
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // byte offset of chunk j of this row inside a raw slot = row_off + ((j ^ swz) << 4): the TMA swizzle
         // (Swizzle<log2(cps),4,3>) XORs address bits [4,4+log2 cps) with bits [7,7+log2 cps)
         const uint32_t row_off = (uint32_t)(row * 16 * CPS);
-        const uint32_t swz = (row_off >> 7) & (uint32_t)(CPS - 1);
+        const uint32_t swz = (row_off >> 7) & (CPS == 4 ? 3u : (CPS == 2 ? 1u : 0u));   // 3 chunks per stage: no swizzle (48-byte rows are conflict-free)
         // multipliers 2^(7-c) of the scaled expansion; derived from a kernel argument so that ptxas keeps them
         // as IMAD operands (FMA pipe) instead of folding them back into ALU-pipe shifts
         uint32_t mult[8];
@@ -800,16 +804,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 const UnitGeo ug = unit_geo<PAIR>(T, u, rank);
                 const int z = T.a_batched ? ug.z : 0;
                 const int row0 = ug.mt * 128;                // may lie beyond the matrix in pair mode: TMA fills zeros
-                for (int w = 0; w < T.bmw; ++w) {
-                    uint32_t m = stage_bits(unit_word<PAIR>(T, u, w, gdk), CPS);
-                    while (m) {
-                        const int c0 = 32 * w + __ffs(m) - 1;   // first chunk of a non-zero stage
-                        m &= m - 1;
-                        mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8, hinted);
-                        mbar_expect_tx(&raw_full[slot], bytes);
-                        tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
-                        if (++slot == kRawSlots) { slot = 0; ++use; }
-                    }
+                for (int st = 0; st < T.nst; ++st) {
+                    if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                    const int c0 = st * CPS;                    // first chunk of a non-zero stage
+                    mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8, hinted);
+                    mbar_expect_tx(&raw_full[slot], bytes);
+                    tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
+                    if (++slot == kRawSlots) { slot = 0; ++use; }
                 }
             }
         }
@@ -841,28 +842,25 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         conv_seen = zi;
                     }
                 }
-                for (int w = 0; w < T.bmw; ++w) {
-                    uint32_t m = stage_bits(unit_word<PAIR>(T, u, w, gdk), CPS);
-                    while (m) {
-                        const int c0 = 32 * w + __ffs(m) - 1;
-                        m &= m - 1;
-                        const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
-                        mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);
-                        if (dbg_no_bulk) {
-                            mbar_arrive(&full[s]);
-                        } else if (PAIR) {
-                            // this CTA's half of every chunk (the image keeps the two halves of a chunk apart)
-                            const uint32_t half_bytes = chunk_bytes >> 1;
-                            mbar_expect_tx(&full[s], half_bytes * (uint32_t)nch);
-                            for (int j = 0; j < nch; ++j)
-                                bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes + (size_t)j * half_bytes,
-                                         img + (unsigned long long)(c0 + j) * chunk_bytes + (unsigned long long)rank * half_bytes, half_bytes, &full[s]);
-                        } else {
-                            mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
-                            bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
-                        }
-                        if (++s == S) { s = 0; ++use; }
+                for (int st = 0; st < T.nst; ++st) {
+                    if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                    const int c0 = st * CPS;
+                    const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
+                    mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);
+                    if (dbg_no_bulk) {
+                        mbar_arrive(&full[s]);
+                    } else if (PAIR) {
+                        // this CTA's half of every chunk (the image keeps the two halves of a chunk apart)
+                        const uint32_t half_bytes = chunk_bytes >> 1;
+                        mbar_expect_tx(&full[s], half_bytes * (uint32_t)nch);
+                        for (int j = 0; j < nch; ++j)
+                            bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes + (size_t)j * half_bytes,
+                                     img + (unsigned long long)(c0 + j) * chunk_bytes + (unsigned long long)rank * half_bytes, half_bytes, &full[s]);
+                    } else {
+                        mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
+                        bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
                     }
+                    if (++s == S) { s = 0; ++use; }
                 }
             }
         }
@@ -945,11 +943,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
                 const int u = group_id + tl * ngroups;
-                for (int bw = 0; bw < T.bmw; ++bw) {
-                  uint32_t sm = stage_bits(unit_word<PAIR>(T, u, bw, gdk), CPS);
-                  for (; sm; sm &= sm - 1, ++item) {
+                for (int st = 0; st < T.nst; ++st) {
+                  if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                  {
                     if (owner == who) {
-                        const int c_first = 32 * bw + __ffs(sm) - 1;       // first chunk of this non-zero stage
+                        const int c_first = st * CPS;                      // first chunk of this non-zero stage
                         if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 0);
                         const uint32_t m_cur = acquire(s, use);
                         if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 1);
@@ -986,6 +984,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                     }
                     if (++owner == T.ni) owner = 0;
                     if (++s == S) { s = 0; ++use; }
+                    ++item;
                   }
                 }
                 if (elect_one()) {   // arrives when this issuer's share of the accumulator is complete
@@ -1142,13 +1141,13 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     Tc05Args T;
     T.g = a;
     T.NP = ((p8(a.N) + 15) / 16) * 16;
-    T.cps = 256 / T.NP;
-    if (T.cps > kMaxCps) T.cps = kMaxCps;
-    if (T.cps < 1) T.cps = 1;
-    if (T.cps == 3) T.cps = 2;   // powers of two only: the TMA swizzle and the expanders' chunk addressing assume it
-    static const int cps_cap = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
-    if (cps_cap && T.cps > cps_cap) T.cps = cps_cap;       // experiment knob: shallower stages, deeper ring
-    if (T.cps > a.gdk) T.cps = a.gdk >= 2 ? 2 : 1;          // short K: do not pad stages with empty chunks
+    // chunks per pipeline item: 256 / N_pad, at most 4 -- three A stages of 128 columns beside the double-buffered
+    // accumulator for N <= 64.  Measured alternative (QGTC_TC05_CPS=3: four stages of three chunks, 2 x 64 + 4 x 96
+    // = 512 columns): 1907 vs 2135 TOPS -- a fourth chunk per item is worth more than a fourth stage.
+    T.cps = T.NP <= 64 ? 4 : (T.NP <= 128 ? 2 : 1);
+    static const int cps_env = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxCps) ? v : 0; }();
+    if (cps_env && cps_env <= T.cps) T.cps = cps_env;       // experiment knob: smaller items (3: four stages for N <= 64)
+    if (T.cps > a.gdk) T.cps = a.gdk;                       // short K: do not pad stages with empty chunks
     T.nst = (a.gdk + T.cps - 1) / T.cps;
     T.wch = T.cps;   // one expander warp per lane quarter takes all chunks of an item
     T.wpi = 4;
