@@ -36,12 +36,19 @@ namespace qgtc {
 
 namespace {
 
-constexpr int kProducerWarps = 16;
-constexpr int kEpilogueWarp0 = 16;
-constexpr int kEpilogueWarps = 8;
-constexpr int kLoaderWarp = 24;
-constexpr int kALoaderWarp = 25;
-constexpr int kMmaWarp = 26;      // first MMA issuer (also allocates TMEM); issuer i is warp kMmaWarp + i
+// Warp layout.  QGTC_TC05_WIDE = 0: 16 expander warps (a warp takes all chunks of its item), 8 epilogue warps, 28 warps,
+// 72 registers.  QGTC_TC05_WIDE = 1: 24 expander warps (two warps per lane quarter share an item's chunks: the stage is
+// filled sooner after it is freed), 4 epilogue warps, 32 warps, 64 registers.
+#ifndef QGTC_TC05_WIDE
+#define QGTC_TC05_WIDE 0
+#endif
+constexpr int kProducerWarps = QGTC_TC05_WIDE ? 24 : 16;
+constexpr int kEpilogueWarp0 = kProducerWarps;
+constexpr int kEpilogueWarps = QGTC_TC05_WIDE ? 4 : 8;
+constexpr int kEpiStep = kEpilogueWarps / 4;   // epilogue warps per TMEM lane quarter: they take the 32-column words round-robin
+constexpr int kLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
+constexpr int kALoaderWarp = kLoaderWarp + 1;
+constexpr int kMmaWarp = kLoaderWarp + 2;      // first MMA issuer (also allocates TMEM); issuer i is warp kMmaWarp + i
 constexpr int kMaxIssuers = 2;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
 constexpr int kMmaWarp2 = kMmaWarp + 1;
 constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
@@ -501,7 +508,7 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
     const int ob = OB > 0 ? OB : ob_rt;
     const unsigned keep = (1u << ob) - 1u;
     const int mx = 1 << ob;
-    for (int w = half; w * 32 < NP; w += 2) {
+    for (int w = half; w * 32 < NP; w += kEpiStep) {
         const bool two = w * 32 + 32 <= NP;          // the tile may end on a 16-column half word
         if (OB >= 4 && two && w * 32 + 32 <= N) {
             // ---- whole 32-column word: transpose path
@@ -657,7 +664,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // warp = (TMEM lane quarter q, slot t).  An item (stage) is expanded by wpi warps, each taking
         // wch chunks; the 16 warps form G = 16 / wpi groups that take the items round-robin, so a warp
         // has G item periods to get through its (latency-bound) wait / expand / store / signal chain.
-        const int q = warp & 3, g = warp >> 2;
+        const int q = warp & 3, t = warp >> 2;
+        const int spi = T.wpi >> 2;                // expander warps per lane quarter and item
+        const int g = t / spi, c0 = (t - g * spi) * T.wch;   // group, first chunk of this warp's share of an item
         // Each warp expands all chunks of its item for its 32 rows (wpi = 4 warps per item: the fixed cost of an
         // item -- two waits, two arrivals, addresses -- is paid once per 32 rows x stage), so the groups of four
         // warps take the items round-robin and a warp has G item periods for its wait / expand / store / signal chain.
@@ -680,11 +689,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 
         int slot = g % kRawSlots, s = g % S;       // raw ring slot and TMEM/B stage of the current item
         uint32_t raw_use = (uint32_t)(g / kRawSlots), use = (uint32_t)(g / S);
-        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)dcols;
+        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + 32 * c0);
         // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
         const int trole = warp == 0 ? 0 : (warp == 1 ? 3 : (warp == 3 ? 4 : (warp == 8 ? 6 : -1)));
         const bool tr = DBG && (trole >= 0 && lane == 0);
-        volatile unsigned char* my_flags = flags + q;
+        volatile unsigned char* my_flags = flags + c0 * 4 + q;
         // expansion of one 128-bit chunk of this lane's row into the 32 TMEM columns' registers
         auto expand = [&](const uint4& pv, uint32_t (&r)[32]) {
             const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -724,7 +733,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes + row_off;
 #pragma unroll
             for (int j = 0; j < kMaxCps; ++j)
-                v[j] = j < WCH ? *reinterpret_cast<const uint4*>(src + (((uint32_t)j ^ swz) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+                v[j] = j < WCH ? *reinterpret_cast<const uint4*>(src + (((uint32_t)(c0 + j) ^ swz) << 4)) : make_uint4(0u, 0u, 0u, 0u);
             if (tr) QGTC_TRACE(trole, k, 1);
             // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
             // stage's previous use drain, so only the tcgen05.st sits behind the wait.  An all-zero 32 x 128 block is
@@ -997,7 +1006,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     } else {
         // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
         // a warp owns the 16-column blocks cb with (cb >> 1) % 2 == half, i.e. every other 32-column word
-        const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;
+        const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;   // half = index among the kEpiStep warps of this lane quarter
         const int M = P.M, N = P.N, ob = P.out_bit;
         const int dshift = amode == 1 ? 7 : (amode == 2 ? 3 : 0);   // the accumulators hold 2^dshift x the sums
         const int wpr = s128(N) * 4;
@@ -1010,7 +1019,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             uint32_t z[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) z[e] = 0u;
-            for (int w32 = half; w32 * 32 < NP; w32 += 2) {
+            for (int w32 = half; w32 * 32 < NP; w32 += kEpiStep) {
                 const uint32_t col = (uint32_t)(b * NP + w32 * 32);
                 if (w32 * 32 + 32 <= NP) tmem_st32(tmem_base + ((uint32_t)(32 * q) << 16) + col, z);
                 else tmem_st16(tmem_base + ((uint32_t)(32 * q) << 16) + col, z);   // NP % 32 == 16: a trailing half word
@@ -1034,7 +1043,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             if (EPI == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out) + (unsigned long long)z * P.out_bstride;
                 for (int cb = 0; cb < NP / 16; ++cb) {
-                    if (((cb >> 1) & 1) != half) continue;
+                    if (((cb >> 1) % kEpiStep) != half) continue;
                     int v[16];
                     tmem_ld16(d_tmem + 16 * cb, v);
                     if (m < M) {
@@ -1149,8 +1158,9 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     if (cps_env && cps_env <= T.cps) T.cps = cps_env;       // experiment knob: smaller items (3: four stages for N <= 64)
     if (T.cps > a.gdk) T.cps = a.gdk;                       // short K: do not pad stages with empty chunks
     T.nst = (a.gdk + T.cps - 1) / T.cps;
-    T.wch = T.cps;   // one expander warp per lane quarter takes all chunks of an item
-    T.wpi = 4;
+    // expander warps per item: one per TMEM lane quarter takes all chunks (wide layout: two per quarter split them)
+    T.wch = (QGTC_TC05_WIDE && T.cps >= 2) ? T.cps / 2 : T.cps;
+    T.wpi = 4 * T.cps / T.wch;
     T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
     int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
