@@ -54,7 +54,9 @@ constexpr int kMmaWarp2 = kMmaWarp + 1;
 constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
 constexpr int kRawSlots = 8;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
 constexpr int kMaxStages = 4;
-constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
+constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage, u8 operand path
+constexpr int kMaxCps4 = 8;       // ... 4-bit operand path (a chunk takes 16 TMEM columns instead of 32)
+constexpr int kSfCols = 8;        // 4-bit path: TMEM columns holding the (all-ones) block scale factors
 constexpr int kTmemCols = 512;
 
 struct Tc05Args {
@@ -79,7 +81,8 @@ struct Tc05Args {
     unsigned int* conv;             // in-kernel feature conversion: [0] = job ticket, [1 + image] = chunks converted; null: prep_b_kernel ran
     uint8_t* bimg_w;                // the image, writable (conversion)
     int conv_images;                // images to convert (1 when every problem aliases one feature matrix)
-    int amode;                      // adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
+    int rslots;                     // raw adjacency ring slots in use (<= kRawSlots)
+    int amode;                      // 3 = 4-bit operand path (kind::mxf4, adjacency bit -> E2M1 nibble, features as E2M1); else adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
     unsigned int* error_flag;       // device word set by the watchdog
@@ -174,6 +177,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::mxf4 (E2M1 x E2M1 -> f32, K = 64) with UE8M0 block scales read from TMEM
+__device__ __forceinline__ void mma_f4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%4], [%5], p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::i8
 __device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -266,6 +278,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16r(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile(
@@ -293,20 +312,27 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int n, int m = 128) {
     return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | (((uint32_t)m >> 4) << 24);
 }
 
+// Block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled), kind::mxf4: A = B = E2M1 (format 1), both
+// K-major, UE8M0 scales, M = 128, K = 64.
+__host__ __device__ constexpr uint32_t make_idesc_f4(int n) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+}
+
 struct SmemLayout {
     // offsets in bytes from the 1024-byte aligned base
     int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, int pair = 0) {
+__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, int pair = 0, int rslots = kRawSlots, int f4 = 0) {
     SmemLayout L;
     L.raw0 = 0;
     L.raw_slot_bytes = 128 * 16 * cps;                 // 2/4/8 KB, keeps every slot 1024-byte aligned for the swizzle
     if (L.raw_slot_bytes < 1024) L.raw_slot_bytes = 1024;
-    L.b_stage0 = L.raw0 + kRawSlots * L.raw_slot_bytes;
-    L.b_stage_bytes = cps * NP * (pair ? 64 : 128);    // pair mode: each CTA holds half of the feature columns
+    L.raw_slot_bytes = (L.raw_slot_bytes + 1023) & ~1023;
+    L.b_stage0 = L.raw0 + rslots * L.raw_slot_bytes;
+    L.b_stage_bytes = cps * NP * ((pair || f4) ? 64 : 128);    // pair mode: each CTA holds half of the feature columns; 4-bit path: half the bytes
     L.bars = L.b_stage0 + stages * L.b_stage_bytes;
     L.flags = L.bars + (3 * kMaxStages + 2 * kRawSlots + 6) * 8;
-    L.misc = L.flags + kMaxStages * 16;
+    L.misc = L.flags + kMaxStages * 32;                // flags: [stage][chunk <= 8][lane quarter]
     L.total = L.misc + 32;
     return L;
 }
@@ -454,6 +480,54 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
     }
 }
 
+// 4-bit operand path: packed feature planes (1 or 2 bits) -> E2M1 nibbles in the MMA's K order.  One K chunk of 128
+// elements is four groups (one per 32-bit word wd of the packed run) of [column block][8 columns][16 B]; the 16 bytes of a
+// column hold, for j = 0..3, the eight nibbles i = 0..7 of the feature at bit j + 4 i of the word, scaled to pair with
+// the adjacency nibble of the expanders (bit j of the nibble = 0.5, 1, 2, 2): feature f in {0..3} is stored as 2 f, f,
+// f / 2, f / 2 -- all exact in E2M1 (codes 0,4,6,7 / 0,2,4,5 / 0,1,2,3) -- so that every product is f itself.
+template <int BIT2>
+__global__ void __launch_bounds__(256) prep_b4_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP) {
+    extern __shared__ uint4 pk4[];   // [bit2][8][ld4]
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const int gdk = P.gdk, n_lim = p8(P.N);
+    const unsigned long long gdk4 = (unsigned long long)gdk * 4;
+    const int ktiles = (gdk + kPrepChunks - 1) / kPrepChunks, nblocks = NP / 8;
+    const int ld4 = kPrepChunks + 1;
+    const uint32_t* pk = reinterpret_cast<const uint32_t*>(pk4);
+    const long long jobs = (long long)P.count * ktiles * nblocks;
+    for (long long job = blockIdx.x; job < jobs; job += gridDim.x) {
+        const int nb = (int)(job % nblocks);
+        const long long t = job / nblocks;
+        const int kt = (int)(t % ktiles), z = (int)(t / ktiles);
+        const int c_base = kt * kPrepChunks, nch = min(kPrepChunks, gdk - c_base);
+        const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
+        for (int i = threadIdx.x; i < BIT2 * 8 * nch; i += blockDim.x) {
+            const int cc = i % nch, r = i / nch, col = r & 7, q = r >> 3, n = nb * 8 + col;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (n < n_lim) w = ldw4(x2, (unsigned long long)q * P.w_offset + (unsigned long long)n * gdk4 + 4ull * (c_base + cc));
+            pk4[(size_t)(q * 8 + col) * ld4 + cc] = w;
+        }
+        __syncthreads();
+        uint8_t* base = img + (unsigned long long)z * gstride + (unsigned long long)c_base * NP * 64;
+        for (int i = threadIdx.x; i < nch * 32; i += blockDim.x) {
+            const int col = i & 7, wd = (i >> 3) & 3, cc = i >> 5;
+            const uint32_t w0 = pk[((size_t)(0 * 8 + col) * ld4 + cc) * 4 + wd];
+            const uint32_t w1 = BIT2 > 1 ? pk[((size_t)(1 * 8 + col) * ld4 + cc) * 4 + wd] : 0u;
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t b0 = (w0 >> j) & 0x11111111u, b1 = (w1 >> j) & 0x11111111u;
+                if (j == 0) o[j] = ((b0 | b1) << 2) | (b1 << 1) | (b0 & b1);          // 2 f : codes 0, 4, 6, 7
+                else if (j == 1) o[j] = (b1 << 2) | ((b0 & ~b1) << 1) | (b0 & b1);    //   f : codes 0, 2, 4, 5
+                else o[j] = b0 | (b1 << 1);                                           // f / 2 : codes 0, 1, 2, 3
+            }
+            *reinterpret_cast<uint4*>(base + (size_t)cc * NP * 64 + (size_t)wd * (NP / 8) * 128 + (size_t)nb * 128 + col * 16) =
+                make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The GEMM kernel
 // ---------------------------------------------------------------------------------------------
@@ -480,16 +554,16 @@ __device__ __forceinline__ uint32_t requant_keep(int acc, int mx, unsigned keep)
 }
 
 // Requantized, masked-to-ob-bits bytes of four accumulators, first one in the low byte.
-// FAST (scaled accumulators = 8 x sum, non-negative, ob <= 4): clamp to 8 (2^ob + 1) so that every value fits a byte,
-// gather the four low bytes with three PRMTs and finish byte-parallel: >> 3; the byte 2^ob + 1 ("above the range")
+// FAST (accumulators = 2^dshift x sum with dshift <= 3, non-negative, ob <= 4): clamp to 2^dshift (2^ob + 1) so that every
+// value fits a byte, gather the four low bytes with three PRMTs and finish byte-parallel: >> dshift; the byte 2^ob + 1 ("above the range")
 // becomes 2^ob - 1, the byte 2^ob becomes 0 (reference kernel.h:31-37,350), everything else passes.
 template <bool NN, bool FAST>
 __device__ __forceinline__ uint32_t requant4(int a0, int a1, int a2, int a3, int dshift, int ob, int mx, unsigned keep) {
     if (FAST) {
-        const int lim = (mx + 1) << 3;
+        const int lim = (mx + 1) << dshift;
         const uint32_t t0 = (uint32_t)min(a0, lim), t1 = (uint32_t)min(a1, lim), t2 = (uint32_t)min(a2, lim), t3 = (uint32_t)min(a3, lim);
         const uint32_t lo = __byte_perm(t0, t1, 0x1140u), hi = __byte_perm(t2, t3, 0x1140u);   // bytes 1..3 of every t are zero
-        uint32_t four = (__byte_perm(lo, hi, 0x5410u) >> 3) & 0x1F1F1F1Fu;
+        uint32_t four = (__byte_perm(lo, hi, 0x5410u) >> dshift) & 0x1F1F1F1Fu;
         const uint32_t over = (four >> ob) & four & 0x01010101u;                                 // bytes equal to 2^ob + 1
         return (four & (keep * 0x01010101u)) | (over * keep);
     }
@@ -501,7 +575,8 @@ __device__ __forceinline__ uint32_t requant4(int a0, int a1, int a2, int a3, int
 // quarter q (one row per lane) and every other 32-column word.  OB > 0 fixes the number of output planes at
 // compile time; OB == 0 takes it from `ob_rt`.  Four or more planes are packed through 8 x 8 bit transposes
 // (22 operations per eight values for all planes) instead of one multiply-gather per plane and four values.
-template <int OB, bool NN, bool FAST>
+// F4: the accumulators are f32 sums (exact non-negative integers < 2^23): the magic-number add turns them into ints
+template <int OB, bool NN, bool FAST, bool F4>
 __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half, int N, int ob_rt, int dshift, uint32_t rmask, bool row_ok,
                                               uint32_t* out_row, unsigned long long opt_offset) {
     constexpr int kPlanes = OB > 0 ? OB : 8;
@@ -515,6 +590,13 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             int v0[16], v1[16];
             tmem_ld16(d_tmem + 32 * w, v0);
             tmem_ld16(d_tmem + 32 * w + 16, v1);
+            if (F4) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    v0[e] = __float_as_int(__int_as_float(v0[e]) + 8388608.0f) - 0x4B000000;
+                    v1[e] = __float_as_int(__int_as_float(v1[e]) + 8388608.0f) - 0x4B000000;
+                }
+            }
             uint32_t xs[4], ys[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -545,6 +627,10 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             const int cb = 2 * w + hcb;
             int v[16];
             tmem_ld16(d_tmem + 16 * cb, v);
+            if (F4) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = __float_as_int(__int_as_float(v[e]) + 8388608.0f) - 0x4B000000;
+            }
             const bool whole = 16 * cb + 16 <= N;   // else: one byte mask per four values
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
@@ -580,7 +666,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     const GemmArgs& P = T.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps;
-    const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0);
+    constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
+    constexpr int kCh = F4 ? kMaxCps4 : kMaxCps;          // chunks per item, compile-time bound
+    constexpr int kChunkCols = F4 ? 16 : 32;              // TMEM columns of one expanded chunk
+    const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0, T.rslots, F4 ? 1 : 0);
     const int rank = PAIR ? (int)cluster_ctarank() : 0;            // 0 = leader (issues the MMAs)
     const int group_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int ngroups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -639,8 +728,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int dcols = T.dbufs * NP;       // accumulators first, then the A stages (32 columns per chunk)
-    const int stage_cols = CPS * 32;
+    const int sf_col = T.dbufs * NP;      // 4-bit path: kSfCols columns of unit block scales after the accumulators
+    const int dcols = T.dbufs * NP + (F4 ? kSfCols : 0);   // accumulators (and scales) first, then the A stages
+    const int stage_cols = CPS * kChunkCols;
 
     const int my_tiles = (T.units - group_id + ngroups - 1) / ngroups;   // work units of this CTA (pair)
     const int n_items = *item_count;      // launch_gemm_tc05 guarantees this fits 31 bits
@@ -674,7 +764,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // them at item X-G), which only implies that item X-2S is done -- no mbarrier phase aliasing -- if G <= S
         // (MMA completion is in item order, see the issuers).  With three stages the fourth group idles.
         const int WCH = T.wch;
-        const int G = min(min(kProducerWarps / T.wpi, S), kRawSlots);
+        const int G = min(min(kProducerWarps / T.wpi, S), T.rslots);
         const int row = 32 * q + lane;             // row of the tile == TMEM lane
         const int my_items = g < G ? (n_items - g + G - 1) / G : 0;   // warps beyond the last group idle
         // byte offset of chunk j of this row inside a raw slot = row_off + ((j ^ swz) << 4): the TMA swizzle
@@ -687,9 +777,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 #pragma unroll
         for (int c = 0; c < 8; ++c) mult[c] = T.one << (7 - c);
 
-        int slot = g % kRawSlots, s = g % S;       // raw ring slot and TMEM/B stage of the current item
-        uint32_t raw_use = (uint32_t)(g / kRawSlots), use = (uint32_t)(g / S);
-        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + 32 * c0);
+        const int rslots = T.rslots;
+        int slot = g % rslots, s = g % S;          // raw ring slot and TMEM/B stage of the current item
+        uint32_t raw_use = (uint32_t)(g / rslots), use = (uint32_t)(g / S);
+        const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + kChunkCols * c0);
         // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
         const int trole = warp == 0 ? 0 : (warp == 1 ? 3 : (warp == 3 ? 4 : (warp == 8 ? 6 : -1)));
         const bool tr = DBG && (trole >= 0 && lane == 0);
@@ -723,16 +814,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 }
             }
         };
+        // 4-bit path: one 128-bit chunk -> 16 registers of eight E2M1 nibbles.  Register 4 wd + j, nibble i = bit j + 4 i of
+        // word wd, left at nibble bit j: 0.5, 1.0 or 2.0 (bit 3 would be the sign: it is moved to bit 2); prep_b4_kernel
+        // scales the feature rows by 2, 1, 0.5, 0.5 so that every product is the feature value itself.
+        auto expand4 = [&](const uint4& pv, uint32_t (&r)[16]) {
+            const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int wd = 0; wd < 4; ++wd) {
+                r[4 * wd + 0] = w[wd] & 0x11111111u;
+                r[4 * wd + 1] = w[wd] & 0x22222222u;
+                r[4 * wd + 2] = w[wd] & 0x44444444u;
+                r[4 * wd + 3] = (w[wd] >> 1) & 0x44444444u;
+            }
+        };
         auto is_nonzero = [&](const uint4& pv) -> bool {
             return nojump || PAIR || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
         };
         for (int k = 0; k < my_items; ++k) {
             if (tr) QGTC_TRACE(trole, k, 0);
             if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7, hinted);
-            uint4 v[kMaxCps];
+            uint4 v[kCh];
             const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes + row_off;
 #pragma unroll
-            for (int j = 0; j < kMaxCps; ++j)
+            for (int j = 0; j < kCh; ++j)
                 v[j] = j < WCH ? *reinterpret_cast<const uint4*>(src + (((uint32_t)(c0 + j) ^ swz) << 4)) : make_uint4(0u, 0u, 0u, 0u);
             if (tr) QGTC_TRACE(trole, k, 1);
             // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
@@ -741,31 +845,51 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // other three lane quarters are zero too.
             unsigned nzmask = 0;
             const uint32_t st_s = st_addr + (uint32_t)(s * stage_cols);
-            {
-                uint32_t r[32];
-                if (is_nonzero(v[0])) nzmask |= 1u;
-                expand(v[0], r);
-                if (tr) QGTC_TRACE(trole, k, 2);
-                mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
-                tc_fence_after();
-                if (tr) QGTC_TRACE(trole, k, 3);
-                if (!dbg_no_st) tmem_st32(st_s, r);
-                else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
-            }
+            if (F4) {
+                {
+                    uint32_t r[16];
+                    if (is_nonzero(v[0])) nzmask |= 1u;
+                    expand4(v[0], r);
+                    mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
+                    tc_fence_after();
+                    tmem_st16r(st_s, r);
+                }
 #pragma unroll
-            for (int j = 1; j < kMaxCps; ++j) {
-                if (j < WCH) {   // warp-uniform
+                for (int j = 1; j < kCh; ++j) {
+                    if (j < WCH) {   // warp-uniform
+                        uint32_t r[16];
+                        if (is_nonzero(v[j])) nzmask |= 1u << j;
+                        expand4(v[j], r);
+                        tmem_st16r(st_s + (uint32_t)(16 * j), r);
+                    }
+                }
+            } else {
+                {
                     uint32_t r[32];
-                    if (is_nonzero(v[j])) nzmask |= 1u << j;
-                    expand(v[j], r);
-                    if (!dbg_no_st) tmem_st32(st_s + (uint32_t)(32 * j), r);
-                    else if (r[5] == 0xdeadbeefu) flags[255] = 1;
+                    if (is_nonzero(v[0])) nzmask |= 1u;
+                    expand(v[0], r);
+                    if (tr) QGTC_TRACE(trole, k, 2);
+                    mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
+                    tc_fence_after();
+                    if (tr) QGTC_TRACE(trole, k, 3);
+                    if (!dbg_no_st) tmem_st32(st_s, r);
+                    else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
+                }
+#pragma unroll
+                for (int j = 1; j < kCh; ++j) {
+                    if (j < WCH) {   // warp-uniform
+                        uint32_t r[32];
+                        if (is_nonzero(v[j])) nzmask |= 1u << j;
+                        expand(v[j], r);
+                        if (!dbg_no_st) tmem_st32(st_s + (uint32_t)(32 * j), r);
+                        else if (r[5] == 0xdeadbeefu) flags[255] = 1;
+                    }
                 }
             }
             // every lane holds its raw words by now (the votes of the expansions needed them): the slot can be refilled
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[slot]);
-            if (lane < WCH) my_flags[s * 16 + lane * 4] = (unsigned char)((nzmask >> lane) & 1u);
+            if (lane < WCH) my_flags[s * 32 + lane * 4] = (unsigned char)((nzmask >> lane) & 1u);
             if (tr) QGTC_TRACE(trole, k, 4);
             if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
@@ -774,7 +898,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             if (lane == 0) mbar_arrive(&full[s]);
             if (tr) QGTC_TRACE(trole, k, 6);
             slot += G;
-            if (slot >= kRawSlots) { slot -= kRawSlots; ++raw_use; }
+            if (slot >= rslots) { slot -= rslots; ++raw_use; }
             s += G;
             if (s >= S) { s -= S; ++use; }
         }
@@ -819,7 +943,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                     mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8, hinted);
                     mbar_expect_tx(&raw_full[slot], bytes);
                     tma_load_3d(raw_slots + (size_t)slot * L.raw_slot_bytes, &tmapA, c0 * 4, row0, z, &raw_full[slot]);
-                    if (++slot == kRawSlots) { slot = 0; ++use; }
+                    if (++slot == T.rslots) { slot = 0; ++use; }
                 }
             }
         }
@@ -829,7 +953,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // programmatic dependent launch: everything up to here (and the adjacency pipeline) overlaps the tail
             // of prep_b_kernel; the image itself is complete and visible only after this wait
             asm volatile("griddepcontrol.wait;\n" ::: "memory");
-            const uint32_t chunk_bytes = (uint32_t)NP * 128u;
+            const uint32_t chunk_bytes = (uint32_t)NP * (F4 ? 64u : 128u);
             int s = 0, conv_seen = -1;
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
@@ -921,15 +1045,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 __trap();
             }
             const uint32_t tb = 0u;
-            const uint32_t idesc = make_idesc_i8(NP, PAIR ? 256 : 128);
+            const uint32_t idesc = F4 ? make_idesc_f4(NP) : make_idesc_i8(NP, PAIR ? 256 : 128);
+            const uint32_t sfa = tb + (uint32_t)sf_col, sfb = tb + (uint32_t)sf_col + 4u;   // 4-bit path: unit scales (every byte 0x7F)
             const uint32_t lbo = (uint32_t)(NP / (PAIR ? 16 : 8)) * 128u, sbo = 128u;   // pair: this CTA's smem holds NP/2 columns
             // descriptor = constant high word | (low word that only differs in the 14-bit start address)
             const uint64_t desc0 = make_smem_desc(smem_u32(b_stages), lbo, sbo);
             const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
             const uint32_t lo0 = (uint32_t)desc0;
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
-            const uint32_t chunk_lo = ((uint32_t)NP * (PAIR ? 64u : 128u)) >> 4;
-            const uint32_t kstep_lo = (2u * lbo) >> 4;
+            const uint32_t chunk_lo = ((uint32_t)NP * ((PAIR || F4) ? 64u : 128u)) >> 4;
+            const uint32_t kstep_lo = (2u * lbo) >> 4;   // one MMA's K: two core matrices (u8: 2 x 16 elements, 4-bit: 2 x 32)
             int s = 0, buf = 0, item = 0, owner = 0;   // owner = item % T.ni
             uint32_t use = 0, duse = 0;
             auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
@@ -942,8 +1067,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 }
                 tc_fence_after();
                 // one word per chunk: the four lane quarters' "non-zero" bytes
-                const uint32_t w = lane < 4 ? *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 16 + lane * 4) : 0u;
-                const uint32_t m4 = __ballot_sync(0xffffffffu, w != 0u) & 0xFu;
+                const uint32_t w = lane < kCh ? *reinterpret_cast<volatile uint32_t*>(smem_raw + L.flags + s_ * 32 + lane * 4) : 0u;
+                const uint32_t m4 = __ballot_sync(0xffffffffu, w != 0u) & ((1u << kCh) - 1u);
                 return dbg_no_mma ? 0u : m4;
             };
             for (int tl = 0; tl < my_tiles; ++tl) {
@@ -965,14 +1090,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
                         if (elect_one()) {
 #pragma unroll
-                            for (int j = 0; j < kMaxCps; ++j) {
+                            for (int j = 0; j < kCh; ++j) {
                                 if (j < nch && ((m_cur >> j) & 1u)) {
+                                    if (F4) {   // two MMAs of K = 64 per 128-bit chunk (8 TMEM columns, two 32-element core matrices each)
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) {
-                                        const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                        const uint32_t d_use = (dbg_alt_d && (ks & 1)) ? (d_tmem ^ (uint32_t)NP) : d_tmem;
-                                        if (PAIR) mma_i8_ts_pair(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
-                                        else mma_i8_ts(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        for (int mm = 0; mm < 2; ++mm) {
+                                            const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)mm * kstep_lo);
+                                            mma_f4_ts(d_tmem, a_tmem + (uint32_t)(16 * j + 8 * mm), desc, idesc, sfa, sfb, 1u);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int ks = 0; ks < 4; ++ks) {
+                                            const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                                            const uint32_t d_use = (dbg_alt_d && (ks & 1)) ? (d_tmem ^ (uint32_t)NP) : d_tmem;
+                                            if (PAIR) mma_i8_ts_pair(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                            else mma_i8_ts(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        }
                                     }
                                 }
                             }
@@ -1008,7 +1141,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // a warp owns the 16-column blocks cb with (cb >> 1) % 2 == half, i.e. every other 32-column word
         const int q = warp & 3, half = (warp - kEpilogueWarp0) >> 2;   // half = index among the kEpiStep warps of this lane quarter
         const int M = P.M, N = P.N, ob = P.out_bit;
-        const int dshift = amode == 1 ? 7 : (amode == 2 ? 3 : 0);   // the accumulators hold 2^dshift x the sums
+        const int dshift = amode == 1 ? 7 : (amode == 2 ? 3 : 0);   // the accumulators hold 2^dshift x the sums (4-bit path: f32 sums)
         const int wpr = s128(N) * 4;
         const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
         int buf = 0;
@@ -1026,6 +1159,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             }
             tmem_wait_st();
         };
+        if (F4 && half == 0) {   // unit UE8M0 block scales (2^0 = 0x7F) in every byte of the scale columns of this lane quarter
+            uint32_t sf[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sf[e] = 0x7F7F7F7Fu;
+            static_assert(kSfCols == 8, "scale columns are written by one x8 store");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)sf_col),
+                         "r"(sf[0]), "r"(sf[1]), "r"(sf[2]), "r"(sf[3]), "r"(sf[4]), "r"(sf[5]), "r"(sf[6]), "r"(sf[7]) : "memory");
+            tmem_wait_st();
+        }
         for (int b = 0; b < T.dbufs; ++b) {
             zero_my_columns(b);
             tc_fence_before();
@@ -1050,7 +1192,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int n = 16 * cb + j;
-                            if (n < N) out[(size_t)m * N + n] = (float)(v[j] >> dshift);
+                            if (n < N) out[(size_t)m * N + n] = F4 ? __int_as_float(v[j]) : (float)(v[j] >> dshift);
                         }
                     }
                 }
@@ -1060,13 +1202,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 const uint32_t rmask = m < M ? 0xffffffffu : 0u;
                 uint32_t* out_row = out + (unsigned long long)m * wpr;
                 // the plane loop is unrolled for the common widths (a runtime bound issues all 8 planes predicated)
-#define QGTC_EPI_CASE(OBV, NNV, FASTV) epi_bits_tile<OBV, NNV, FASTV>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
-                if (dshift == 3 && ob <= 4) {   // expansion mode 2: accumulators = 8 x sums, non-negative; byte-parallel requantize
+#define QGTC_EPI_CASE(OBV, NNV, FASTV) epi_bits_tile<OBV, NNV, FASTV, F4>(d_tmem, NP, half, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
+                if (F4 || dshift == 3) {   // 4-bit path (exact sums) / expansion mode 2 (8 x sums): non-negative; byte-parallel requantize up to 4 bits
                     switch (ob) {
                         case 1: QGTC_EPI_CASE(1, true, true); break;
                         case 2: QGTC_EPI_CASE(2, true, true); break;
                         case 4: QGTC_EPI_CASE(4, true, true); break;
-                        default: QGTC_EPI_CASE(0, true, true); break;
+                        case 8: QGTC_EPI_CASE(8, true, false); break;
+                        default: if (ob <= 4) QGTC_EPI_CASE(0, true, true); else QGTC_EPI_CASE(0, true, false); break;
                     }
                 } else if (dshift > 0) {   // scaled expansion: sums cannot wrap, accumulators are non-negative
                     switch (ob) {
@@ -1150,32 +1293,49 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     Tc05Args T;
     T.g = a;
     T.NP = ((p8(a.N) + 15) / 16) * 16;
-    // chunks per pipeline item: 256 / N_pad, at most 4 -- three A stages of 128 columns beside the double-buffered
-    // accumulator for N <= 64.  Measured alternative (QGTC_TC05_CPS=3: four stages of three chunks, 2 x 64 + 4 x 96
-    // = 512 columns): 1907 vs 2135 TOPS -- a fourth chunk per item is worth more than a fourth stage.
-    T.cps = T.NP <= 64 ? 4 : (T.NP <= 128 ? 2 : 1);
-    static const int cps_env = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxCps) ? v : 0; }();
-    if (cps_env && cps_env <= T.cps) T.cps = cps_env;       // experiment knob: smaller items (3: four stages for N <= 64)
-    if (T.cps > a.gdk) T.cps = a.gdk;                       // short K: do not pad stages with empty chunks
-    T.nst = (a.gdk + T.cps - 1) / T.cps;
-    // expander warps per item: one per TMEM lane quarter takes all chunks (wide layout: two per quarter split them)
-    T.wch = (QGTC_TC05_WIDE && T.cps >= 2) ? T.cps / 2 : T.cps;
-    T.wpi = 4 * T.cps / T.wch;
-    T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
-    int stages = (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
-    if (stages > kMaxStages) stages = kMaxStages;
     static const bool pair_env = [] { const char* e = getenv("QGTC_TC05_PAIR"); return e && e[0] == '1'; }();
     // pair mode (opt-in: QGTC_FLAG_TC05_PAIR or QGTC_TC05_PAIR=1): two CTAs of a cluster share every MMA
     // (cta_group::2, M = 256) and each streams half of the feature image.  Measured on B200 it does not beat the
     // single-CTA form (the adjacency expanders, not the tensor front end or L2, bound the kernel): DESIGN.md 5.4.
     const bool pair = (pair_env || (a.flags & QGTC_FLAG_TC05_PAIR)) && (T.NP % 16 == 0) && ((long long)((p8(a.M) + 127) / 128) * a.count >= 2);
+    // 4-bit operand path (kind::mxf4, K = 64 per MMA; QGTC_TC05_FP4=0 disables): features of at most 2 bits are exact in
+    // E2M1 with the row scaling of prep_b4_kernel, the f32 accumulators hold exact sums below 2^23.  Half the TMEM per
+    // chunk: items of up to 7 chunks in three stages next to the double-buffered accumulator and the scale columns.
+    static const bool f4_env = [] { const char* e = getenv("QGTC_TC05_FP4"); return !(e && e[0] == '0'); }();
+    static const bool trace_env = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
+    const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
+    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && T.NP <= 64 && max_sum < 8388608.0;
+    if (f4) {
+        // chunks per item: the largest of {7, 5, 4, 3, 2, 1} that fits three stages and K (6 and 8 chunks would put the
+        // 128 rows of a raw slot on a stride with shared-memory bank conflicts; 4 and 2 use the TMA swizzle)
+        const int cap = (kTmemCols - 2 * T.NP - kSfCols) / 48;
+        const int lim = cap < a.gdk ? cap : a.gdk;
+        T.cps = lim >= 7 ? 7 : (lim >= 5 ? 5 : lim);
+        T.amode = 3;
+    } else {
+        // chunks per pipeline item: 256 / N_pad, at most 4 -- three A stages of 128 columns beside the double-buffered
+        // accumulator for N <= 64.  Measured alternative (QGTC_TC05_CPS=3: four stages of three chunks, 2 x 64 + 4 x 96
+        // = 512 columns): 1907 vs 2135 TOPS -- a fourth chunk per item is worth more than a fourth stage.
+        T.cps = T.NP <= 64 ? 4 : (T.NP <= 128 ? 2 : 1);
+        static const int cps_env = [] { const char* e = getenv("QGTC_TC05_CPS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxCps) ? v : 0; }();
+        if (cps_env && cps_env <= T.cps) T.cps = cps_env;       // experiment knob: smaller items (3: four stages for N <= 64)
+        if (T.cps > a.gdk) T.cps = a.gdk;                       // short K: do not pad stages with empty chunks
+    }
+    T.nst = (a.gdk + T.cps - 1) / T.cps;
+    // expander warps per item: one per TMEM lane quarter takes all chunks (wide layout: two per quarter split them)
+    T.wch = (QGTC_TC05_WIDE && !f4 && T.cps >= 2) ? T.cps / 2 : T.cps;
+    T.wpi = 4 * T.cps / T.wch;
+    T.dbufs = f4 ? 2 : ((2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1);
+    int stages = f4 ? (kTmemCols - 2 * T.NP - kSfCols) / (T.cps * 16) : (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
+    if (stages > kMaxStages) stages = kMaxStages;
+    T.rslots = f4 ? 6 : kRawSlots;      // 4-bit path: raw slots are up to 14 KB
     // in-kernel feature conversion (opt-in: QGTC_TC05_CONV=1; default is the separate prep_b_kernel): needs an expander
     // group without items (fewer than four stages).  Measured on B200 (4096 x 4096 x 64,
     // 96 graphs): the GEMM kernel is bound by its ALU / issue slots, so the converters' instructions cost more inside it
     // (+17 us at 1 bit, +83 us at 8 bits) than prep_b_kernel and its launch gap cost outside (15 / 29 us).
     static const bool conv_env = [] { const char* e = getenv("QGTC_TC05_CONV"); return e && e[0] == '1'; }();
     const bool conv_want = conv_env && !pair;
-    while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair).total > 200 * 1024) --stages;
+    while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair, T.rslots, f4).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
     T.mtiles = (p8(a.M) + 127) / 128;
@@ -1189,9 +1349,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         T.ni = (ni_env >= 1 && ni_env <= kMaxIssuers) ? ni_env : 2;
         if (pair && T.ni < 2) T.ni = 2;   // the peer CTA's first two issuer warps are its relays
     }
-    {   // expansion mode: the scaled sums must fit an int32 (mode 1: K < 65793 for 8-bit features)
+    if (!f4) {   // expansion mode: the scaled sums must fit an int32 (mode 1: K < 65793 for 8-bit features)
         static const int amode_env = [] { const char* e = getenv("QGTC_TC05_AMODE"); return e ? atoi(e) : -1; }();
-        const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
         const bool ok2 = a.bit2 <= 5 && max_sum * 8.0 < 2147483648.0, ok1 = max_sum * 128.0 < 2147483648.0;
         T.amode = ok2 ? 2 : (ok1 ? 1 : 0);
         if (amode_env == 0 || (amode_env == 1 && ok1) || (amode_env == 2 && ok2)) T.amode = amode_env;   // experiment knob
@@ -1200,7 +1359,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.bmw = (a.gdk + 31) / 32;
     if ((long long)((T.total_tiles + kNumSMs - 1) / kNumSMs + 1) * T.nst > (1ll << 30)) return QGTC_ERR_UNSUPPORTED;
     const bool b_shared = a.count > 1 && a.x2_bstride == 0;   // every problem aliases one feature matrix: one image
-    T.bimg_gstride = b_shared ? 0ull : (unsigned long long)a.gdk * T.NP * 128;
+    const unsigned long long chunk_img_bytes = (unsigned long long)T.NP * (f4 ? 64 : 128);   // image bytes of one 128-element K chunk
+    T.bimg_gstride = b_shared ? 0ull : (unsigned long long)a.gdk * chunk_img_bytes;
 
     // tensor map of the packed adjacency: uint32 [count][P8(M)][gdk*4], box = [1][128][4*cps]
     alignas(64) CUtensorMap tmap;
@@ -1248,8 +1408,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     }
     uint8_t* img = nullptr;
     const int img_problems = b_shared ? 1 : a.count;
-    const size_t img_bytes = (((size_t)a.gdk * T.NP * 128 * img_problems) + 255) & ~(size_t)255;
-    const bool conv = conv_want && T.stages < kProducerWarps / T.wpi;    // an idle expander group exists
+    const size_t img_bytes = (((size_t)a.gdk * chunk_img_bytes * img_problems) + 255) & ~(size_t)255;
+    const bool conv = conv_want && !f4 && T.stages < kProducerWarps / T.wpi;    // an idle expander group exists
     const size_t conv_bytes = conv ? (size_t)(1 + img_problems) * sizeof(unsigned int) : 0;
     e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes + conv_bytes, st);
     if (e != cudaSuccess) return record_cuda_error(e, "cudaMallocAsync(feature image)");
@@ -1269,8 +1429,12 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         long long pgrid = (long long)img_problems * ((a.gdk + kPrepChunks - 1) / kPrepChunks) * (T.NP / 8);
         if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
         const size_t psmem = (size_t)a.bit2 * 8 * (kPrepChunks + 1) * sizeof(uint4);    // <= 33 KB
-        const unsigned long long gs = (unsigned long long)a.gdk * T.NP * 128;
+        const unsigned long long gs = (unsigned long long)a.gdk * chunk_img_bytes;
         const int halves = pair ? 2 : 1;
+        if (f4) {
+            if (a.bit2 == 1) prep_b4_kernel<1><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP);
+            else prep_b4_kernel<2><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP);
+        } else
 #define QGTC_PREP(B)                                                                              \
     case B:                                                                                       \
         if (T.amode == 2) prep_b_kernel<B, true><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP, halves); \
@@ -1286,7 +1450,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     }
 
     if (rc == QGTC_OK) {
-        const int smem = smem_layout(T.NP, T.stages, T.cps, pair).total + 1024;
+        const int smem = smem_layout(T.NP, T.stages, T.cps, pair, T.rslots, f4).total + 1024;
         const int groups = pair ? (T.units < kNumSMs / 2 ? T.units : kNumSMs / 2) : (T.units < kNumSMs ? T.units : kNumSMs);
         auto launch = [&](auto kfn) -> int {
             cudaError_t e2 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1324,6 +1488,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             else rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
         } else if (pair) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, 0, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, 0, -1>);
+        } else if (T.amode == 3) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 3>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 3>);
         } else if (trace && !fl && T.amode == 2) {
             rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2>);       // the production code path + clock reads
         } else if (trace) {
