@@ -1304,7 +1304,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     static const bool f4_env = [] { const char* e = getenv("QGTC_TC05_FP4"); return !(e && e[0] == '0'); }();
     static const bool trace_env = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
     const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
-    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && T.NP <= 64 && max_sum < 8388608.0;
+    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && T.NP <= 128 && max_sum < 8388608.0;
     if (f4) {
         // chunks per item: the largest of {7, 5, 4, 3, 2, 1} that fits three stages and K (6 and 8 chunks would put the
         // 128 rows of a raw slot on a stride with shared-memory bank conflicts; 4 and 2 use the TMA swizzle)
