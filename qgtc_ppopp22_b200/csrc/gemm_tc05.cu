@@ -1311,6 +1311,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         const int cap = (kTmemCols - 2 * T.NP - kSfCols) / 48;
         const int lim = cap < a.gdk ? cap : a.gdk;
         T.cps = lim >= 7 ? 7 : (lim >= 5 ? 5 : lim);
+        static const int cps4_env = [] { const char* e = getenv("QGTC_TC05_CPS4"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 3 || v == 4 || v == 5 || v == 7) ? v : 0; }();
+        if (cps4_env && cps4_env <= T.cps) T.cps = cps4_env;   // experiment knob
         T.amode = 3;
     } else {
         // chunks per pipeline item: 256 / N_pad, at most 4 -- three A stages of 128 columns beside the double-buffered
