@@ -181,15 +181,16 @@ sys.exit(1 if bad else 0)
 """
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, "fp4"])
 def test_tc05_expansion_modes_agree(mode):
-    """The three adjacency expansion modes of the tcgen05 engine (plain shift + AND, x128 multiply + AND, AND-only with
-    pre-scaled feature rows) are chosen by operand range; QGTC_TC05_AMODE (read once per process) forces one where it
-    is exact, so each runs in its own interpreter against the mma.sync engine."""
+    """The operand paths of the tcgen05 engine -- u8 with the three adjacency expansion modes (plain shift + AND, x128
+    multiply + AND, AND-only with pre-scaled feature rows) and the 4-bit kind::mxf4 path for features of at most 2 bits --
+    are chosen by operand range; QGTC_TC05_AMODE / QGTC_TC05_FP4 (read once per process) force one where it is exact, so
+    each runs in its own interpreter against the mma.sync engine."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, QGTC_TC05_AMODE=str(mode))
+    env = dict(os.environ, QGTC_TC05_FP4="1") if mode == "fp4" else dict(os.environ, QGTC_TC05_AMODE=str(mode), QGTC_TC05_FP4="0")
     r = subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
