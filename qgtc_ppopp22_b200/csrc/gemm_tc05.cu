@@ -56,7 +56,7 @@ constexpr int kRawSlots = 8;      // TMA ring of packed adjacency tiles (128 row
 constexpr int kMaxStages = 4;
 constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage, u8 operand path
 constexpr int kMaxCps4 = 8;       // ... 4-bit operand path (a chunk takes 16 TMEM columns instead of 32)
-constexpr int kSfCols = 8;        // 4-bit path: TMEM columns holding the (all-ones) block scale factors
+constexpr int kSfCols = 16;       // 4-bit path: TMEM columns holding the (all-ones) block scale factors: 4 for A, 12 for B (N up to 256)
 constexpr int kTmemCols = 512;
 
 struct Tc05Args {
@@ -1163,9 +1163,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             uint32_t sf[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) sf[e] = 0x7F7F7F7Fu;
-            static_assert(kSfCols == 8, "scale columns are written by one x8 store");
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)sf_col),
-                         "r"(sf[0]), "r"(sf[1]), "r"(sf[2]), "r"(sf[3]), "r"(sf[4]), "r"(sf[5]), "r"(sf[6]), "r"(sf[7]) : "memory");
+            static_assert(kSfCols == 16, "scale columns are written by one x16 store");
+            tmem_st16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)sf_col, sf);
             tmem_wait_st();
         }
         for (int b = 0; b < T.dbufs; ++b) {
@@ -1304,11 +1303,15 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     static const bool f4_env = [] { const char* e = getenv("QGTC_TC05_FP4"); return !(e && e[0] == '0'); }();
     static const bool trace_env = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
     const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
-    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && T.NP <= 128 && max_sum < 8388608.0;
+    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && max_sum < 8388608.0;
     if (f4) {
         // chunks per item: the largest of {7, 5, 4, 3, 2, 1} that fits three stages and K (6 and 8 chunks would put the
         // 128 rows of a raw slot on a stride with shared-memory bank conflicts; 4 and 2 use the TMA swizzle)
-        const int cap = (kTmemCols - 2 * T.NP - kSfCols) / 48;
+        // accumulators: double-buffered up to N = 128, single above (as on the u8 path)
+        T.dbufs = T.NP <= 128 ? 2 : 1;
+        int cap = (kTmemCols - T.dbufs * T.NP - kSfCols) / 48;
+        const int smem_cap = (180 * 1024) / (3 * (T.NP * 64 + 2 * 128 * 16));   // three feature stages + six raw slots per chunk of an item
+        if (cap > smem_cap) cap = smem_cap;
         const int lim = cap < a.gdk ? cap : a.gdk;
         T.cps = lim >= 7 ? 7 : (lim >= 5 ? 5 : lim);
         static const int cps4_env = [] { const char* e = getenv("QGTC_TC05_CPS4"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 3 || v == 4 || v == 5 || v == 7) ? v : 0; }();
@@ -1327,8 +1330,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     // expander warps per item: one per TMEM lane quarter takes all chunks (wide layout: two per quarter split them)
     T.wch = (QGTC_TC05_WIDE && !f4 && T.cps >= 2) ? T.cps / 2 : T.cps;
     T.wpi = 4 * T.cps / T.wch;
-    T.dbufs = f4 ? 2 : ((2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1);
-    int stages = f4 ? (kTmemCols - 2 * T.NP - kSfCols) / (T.cps * 16) : (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
+    if (!f4) T.dbufs = (2 * T.NP + 2 * T.cps * 32 <= kTmemCols) ? 2 : 1;
+    int stages = f4 ? (kTmemCols - T.dbufs * T.NP - kSfCols) / (T.cps * 16) : (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
     T.rslots = f4 ? 6 : kRawSlots;      // 4-bit path: raw slots are up to 14 KB
     // in-kernel feature conversion (opt-in: QGTC_TC05_CONV=1; default is the separate prep_b_kernel): needs an expander

@@ -28,6 +28,7 @@ CASES = [
     (128, 128, 16, 1, 1), (128, 256, 64, 2, 2), (8, 128, 8, 1, 1), (3, 3, 3, 2, 2), (300, 1000, 40, 2, 2),
     (759, 759, 16, 2, 2), (515, 515, 29, 2, 2), (2258, 2258, 128, 2, 2), (1000, 3000, 121, 4, 4),
     (257, 129, 200, 8, 8), (130, 513, 256, 3, 5), (1024, 1024, 32, 4, 4), (2048, 2048, 64, 8, 8), (640, 4096, 48, 5, 3),
+    (257, 640, 200, 2, 2), (384, 1024, 256, 1, 1), (300, 2000, 144, 2, 2), (520, 1500, 96, 1, 2),
 ]
 
 
