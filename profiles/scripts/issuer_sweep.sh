@@ -1,6 +1,6 @@
 #!/bin/bash
 # tcgen05 engine with 1..4 MMA issuer warps (QGTC_TC05_ISSUERS): batched 4096x4096xN, 2-bit features
-for ni in 2 3; do
+for ni in 1 2; do
   echo "issuers=$ni"
   QGTC_TC05_ISSUERS=$ni python - <<'PY'
 import sys, os, json
