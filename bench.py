@@ -358,6 +358,9 @@ def cluster_gcn_epoch(world, rank):
     a = drv.build_parser().parse_args(base + ["--cuda-graph"])
     r = drv.run(a, graph=g, quiet=True)
     out["epoch_ms_cuda_graph"] = round(r["epoch_ms"], 3)
+    a = drv.build_parser().parse_args(base + ["--cuda-graph", "--streams", "16"])
+    r = drv.run(a, graph=g, quiet=True)
+    out["epoch_ms_cuda_graph_16_streams"] = round(r["epoch_ms"], 3)
     a = drv.build_parser().parse_args(base + ["--cuda-graph", "--streams", "8"] + (["--cpu-baseline"] if rank == 0 else []))
     r = drv.run(a, graph=g, quiet=True)
     out["epoch_ms_cuda_graph_8_streams"] = round(r["epoch_ms"], 3)
