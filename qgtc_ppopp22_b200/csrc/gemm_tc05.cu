@@ -82,6 +82,7 @@ struct Tc05Args {
     uint8_t* bimg_w;                // the image, writable (conversion)
     int conv_images;                // images to convert (1 when every problem aliases one feature matrix)
     int rslots;                     // raw adjacency ring slots in use (<= kRawSlots)
+    unsigned int cps_inv;           // ceil(2^32 / cps): stage of a chunk by one multiply
     int amode;                      // 3 = 4-bit operand path (kind::mxf4, adjacency bit -> E2M1 nibble, features as E2M1); else adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
@@ -368,16 +369,35 @@ __device__ __forceinline__ uint32_t unit_word(const Tc05Args& T, int u, int w, i
     return r;
 }
 
-// Zero-tile jumping from the precomputed bitmap: stage st (chunks [st * cps, st * cps + cps), any cps) of a unit is
-// visited iff one of its chunk bits is set; without a bitmap every stage is.  Every role walks the stages with this.
-template <bool PAIR>
-__device__ __forceinline__ bool stage_present(const Tc05Args& T, int u, int st, int cps, int gdk) {
-    if (!T.bitmap) return true;
-    const int c = st * cps, w = c >> 5, sh = c & 31;
-    uint32_t bits = unit_word<PAIR>(T, u, w, gdk) >> sh;
-    if (sh + cps > 32 && w + 1 < T.bmw) bits |= unit_word<PAIR>(T, u, w + 1, gdk) << (32 - sh);
-    return (bits & ((1u << cps) - 1u)) != 0u;
-}
+// Zero-tile jumping from the precomputed bitmap: a stage (chunks [st * cps, st * cps + cps), any cps) of a unit is
+// visited iff one of its chunk bits is set; without a bitmap every stage is.  Every role walks the stages of a unit with
+// this iterator, so they all see the same item sequence.  With a bitmap the walk costs one find-first-set per NON-ZERO
+// stage (all-zero words are skipped 32 chunks at a time), which is what keeps very sparse inputs fast.
+struct StageIter {
+    int w, st_next, covered_end;   // current bitmap word, next stage (no bitmap), first chunk not yet covered by an emitted stage
+    uint32_t m;                    // chunk bits of word w still to visit
+    __device__ __forceinline__ void begin() { w = -1; st_next = 0; covered_end = 0; m = 0u; }
+    // next non-zero stage of unit u, or -1
+    template <bool PAIR>
+    __device__ __forceinline__ int next(const Tc05Args& T, int u, int cps, int gdk) {
+        if (!T.bitmap) return st_next < T.nst ? st_next++ : -1;
+        for (;;) {
+            if (m == 0u) {
+                if (++w >= T.bmw) return -1;
+                m = unit_word<PAIR>(T, u, w, gdk);
+                const int n = covered_end - 32 * w;          // chunks of this word already inside the last emitted stage
+                if (n > 0) m &= n >= 32 ? 0u : ~((1u << n) - 1u);
+                continue;
+            }
+            const int c = 32 * w + __ffs(m) - 1;
+            const int st = T.cps_inv ? (int)__umulhi((unsigned)c, T.cps_inv) : c;   // c / cps (cps_inv = ceil(2^32 / cps), exact for c < 2^28; 0: cps == 1)
+            covered_end = (st + 1) * cps;
+            const int n = covered_end - 32 * w;
+            m &= n >= 32 ? 0u : ~((1u << n) - 1u);
+            return st;
+        }
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Feature image: X2 (packed planes, raw words, zero-extension) -> u8 values in the MMA's K order,
@@ -717,9 +737,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     {
         const int units_here = (T.units - group_id + ngroups - 1) / ngroups;
         int cnt = 0;
-        for (int i = threadIdx.x; i < units_here * T.nst; i += blockDim.x) {
-            const int ul = i / T.nst, st = i - ul * T.nst;
-            cnt += stage_present<PAIR>(T, group_id + ul * ngroups, st, T.cps, P.gdk) ? 1 : 0;
+        if (!T.bitmap) {
+            if (threadIdx.x == 0) cnt = units_here * T.nst;
+        } else {
+            for (int ul = threadIdx.x; ul < units_here; ul += blockDim.x) {
+                StageIter it;
+                it.begin();
+                while (it.next<PAIR>(T, group_id + ul * ngroups, T.cps, P.gdk) >= 0) ++cnt;
+            }
         }
         if (cnt) atomicAdd(item_count, cnt);
     }
@@ -937,8 +962,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 const UnitGeo ug = unit_geo<PAIR>(T, u, rank);
                 const int z = T.a_batched ? ug.z : 0;
                 const int row0 = ug.mt * 128;                // may lie beyond the matrix in pair mode: TMA fills zeros
-                for (int st = 0; st < T.nst; ++st) {
-                    if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                StageIter it;
+                it.begin();
+                for (int st; (st = it.next<PAIR>(T, u, CPS, gdk)) >= 0;) {
                     const int c0 = st * CPS;                    // first chunk of a non-zero stage
                     mbar_wait<128>(&raw_empty[slot], (use & 1) ^ 1, T.error_flag, 8, hinted);
                     mbar_expect_tx(&raw_full[slot], bytes);
@@ -975,8 +1001,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         conv_seen = zi;
                     }
                 }
-                for (int st = 0; st < T.nst; ++st) {
-                    if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                StageIter it;
+                it.begin();
+                for (int st; (st = it.next<PAIR>(T, u, CPS, gdk)) >= 0;) {
                     const int c0 = st * CPS;
                     const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
                     mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);
@@ -1077,8 +1104,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(buf * NP);
                 const int u = group_id + tl * ngroups;
-                for (int st = 0; st < T.nst; ++st) {
-                  if (!stage_present<PAIR>(T, u, st, CPS, gdk)) continue;
+                StageIter it;
+                it.begin();
+                for (int st; (st = it.next<PAIR>(T, u, CPS, gdk)) >= 0;) {
                   {
                     if (owner == who) {
                         const int c_first = st * CPS;                      // first chunk of this non-zero stage
@@ -1327,6 +1355,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         if (T.cps > a.gdk) T.cps = a.gdk;                       // short K: do not pad stages with empty chunks
     }
     T.nst = (a.gdk + T.cps - 1) / T.cps;
+    T.cps_inv = T.cps == 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)T.cps - 1ull) / (unsigned long long)T.cps);
     // expander warps per item: one per TMEM lane quarter takes all chunks (wide layout: two per quarter split them)
     T.wch = (QGTC_TC05_WIDE && !f4 && T.cps >= 2) ? T.cps / 2 : T.cps;
     T.wpi = 4 * T.cps / T.wch;
