@@ -78,9 +78,6 @@ struct Tc05Args {
     int a_batched;                  // 1: the tensor map's third coordinate is the problem index
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
     int bmw;                        // bitmap words per tile = ceil(gdk / 32)
-    unsigned int* conv;             // in-kernel feature conversion: [0] = job ticket, [1 + image] = chunks converted; null: prep_b_kernel ran
-    uint8_t* bimg_w;                // the image, writable (conversion)
-    int conv_images;                // images to convert (1 when every problem aliases one feature matrix)
     int rslots;                     // raw adjacency ring slots in use (<= kRawSlots)
     unsigned int cps_inv;           // ceil(2^32 / cps): stage of a chunk by one multiply
     int amode;                      // 3 = 4-bit operand path (kind::mxf4, adjacency bit -> E2M1 nibble, features as E2M1); else adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
@@ -158,11 +155,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
             __trap();
         }
     }
-}
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -404,41 +396,6 @@ struct StageIter {
 // laid out as the exact shared-memory image of each 128-element K chunk (core matrices of 8 rows
 // x 16 bytes; K-direction stride (NP/8)*128 B, N-direction stride 128 B).
 // ---------------------------------------------------------------------------------------------
-// One 128-element K chunk c of problem z: packed planes -> the chunk's 128 x NP byte image.  Thread tid of `nthreads`
-// produces the 16-byte items (k group 0..7, column n) with n fastest, so the stores of a warp are one contiguous
-// 512-byte run of the image.  Every item reads its plane words straight from global memory (__ldg, L1-cached: the
-// eight k groups of a column share one 16-byte run of each plane) -- no staging, no barriers, every thread independent.
-__device__ __forceinline__ void convert_chunk(const GemmArgs& P, int z, int c, uint8_t* __restrict__ chunk_img, int NP, int halves, int amode,
-                                              int tid, int nthreads) {
-    const int n_lim = p8(P.N), bit2 = P.bit2;
-    const unsigned long long gdk4 = (unsigned long long)P.gdk * 4;
-    const int nh = NP / halves;
-    const Words x2{P.x2 + (unsigned long long)z * P.x2_bstride, P.x2_words};
-    for (int i = tid; i < 8 * NP; i += nthreads) {
-        const int kg = i / NP, n = i - kg * NP, s = kg >> 1, j0 = (kg & 1) * 4;
-        uint32_t o[4] = {0u, 0u, 0u, 0u};
-        // byte i of o[j] = value of K element (32 s + 4 (j0 + j) + i) = sum over planes of bit (j0 + j + 8 i) of the
-        // plane's word s, shifted to bit q (+ 3 - j in expansion mode 2: the expanders leave adjacency bit c at
-        // 2^(c % 4), the rows carry the complementary factor).  One shift and one AND-OR per (plane, j).
-        if (n < n_lim) {
-            const unsigned long long idx0 = (unsigned long long)n * gdk4 + 4ull * c + s;
-            for (int q = 0; q < bit2; ++q) {
-                const uint32_t w = ldw(x2, (unsigned long long)q * P.w_offset + idx0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int to = q + (amode == 2 ? 3 - j : 0), from = j0 + j;   // bit `from` of every byte -> bit `to`
-                    const uint32_t sh = to >= from ? (w << (to - from)) : (w >> (from - to));
-                    o[j] |= sh & (0x01010101u << to);
-                }
-            }
-        }
-        // image of one K chunk: [half][k group (8)][column block][8 columns][16 B]; halves == 2 in pair mode
-        const int h = n / nh, nl = n - h * nh;
-        *reinterpret_cast<uint4*>(chunk_img + (size_t)h * nh * 128 + (size_t)kg * (nh / 8) * 128 + (size_t)(nl >> 3) * 128 + (nl & 7) * 16) =
-            make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
-
 constexpr int kPrepChunks = 32;   // K chunks per prep job: 512 contiguous bytes of every (plane, column) run
 
 // BIT2 = number of feature planes, MODE2 = expansion mode 2 (rows scaled by 2^(3 - c % 4)): both fixed at compile time so
@@ -927,30 +884,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             s += G;
             if (s >= S) { s -= S; ++use; }
         }
-        if (!PAIR && T.conv != nullptr && g == G) {
-            // ===================== feature converters (the expander group without items) =====================
-            // The four warps turn packed feature planes into the byte image the MMAs read, one 128-element K
-            // chunk per job, jobs handed out by a global ticket in (image, chunk) order across all CTAs; the
-            // feature loaders wait for "all chunks of my problem's image are done".  Converters wait on nothing
-            // but each other (named barrier 1), so they cannot deadlock the pipeline they feed.
-            volatile int* ticket_slot = reinterpret_cast<volatile int*>(smem_raw + L.misc + 20);
-            const int ctid = (warp - 4 * G) * 32 + lane;
-            const int total_jobs = T.conv_images * gdk;
-            const unsigned long long img_stride = (unsigned long long)gdk * NP * 128;
-            auto csync = [] { asm volatile("bar.sync 1, 128;\n" ::: "memory"); };
-            for (;;) {
-                if (ctid == 0) *ticket_slot = (int)atomicAdd(&T.conv[0], 1u);
-                csync();
-                const int job = *ticket_slot;
-                if (job >= total_jobs) break;
-                const int zi = job / gdk, c = job - zi * gdk;
-                convert_chunk(P, zi, c, T.bimg_w + (unsigned long long)zi * img_stride + (unsigned long long)c * NP * 128, NP, 1, amode, ctid, 128);
-                __threadfence();                                              // this thread's stores, GPU scope ...
-                asm volatile("fence.proxy.async.global;\n" ::: "memory");     // ... and towards the async proxy (bulk copies read them)
-                csync();
-                if (ctid == 0) atomicAdd(&T.conv[1 + zi], 1u);
-            }
-        }
     } else if (warp == kALoaderWarp) {
         // ===================== adjacency TMA loader =====================
         if (lane == 0 && !dbg_no_ldg) {
@@ -980,27 +913,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // of prep_b_kernel; the image itself is complete and visible only after this wait
             asm volatile("griddepcontrol.wait;\n" ::: "memory");
             const uint32_t chunk_bytes = (uint32_t)NP * (F4 ? 64u : 128u);
-            int s = 0, conv_seen = -1;
+            int s = 0;
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int u = group_id + tl * ngroups;
                 const int z = unit_geo<PAIR>(T, u, rank).z;
                 const uint8_t* img = T.bimg + (unsigned long long)z * T.bimg_gstride;
-                if (!PAIR && T.conv != nullptr) {   // in-kernel conversion: wait until every chunk of this problem's image is written
-                    const int zi = T.bimg_gstride ? z : 0;
-                    if (zi != conv_seen) {
-                        uint32_t spins = 0;
-                        while (ld_acquire_gpu(T.conv + 1 + zi) < (unsigned)gdk) {
-                            __nanosleep(200);
-                            if (++spins > (1u << 24)) {
-                                if (T.error_flag) { atomicExch_system(T.error_flag, 0x80000000u | 15u); __threadfence_system(); }
-                                __trap();
-                            }
-                        }
-                        asm volatile("fence.proxy.async.global;\n" ::: "memory");
-                        conv_seen = zi;
-                    }
-                }
                 StageIter it;
                 it.begin();
                 for (int st; (st = it.next<PAIR>(T, u, CPS, gdk)) >= 0;) {
@@ -1363,12 +1281,9 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     int stages = f4 ? (kTmemCols - T.dbufs * T.NP - kSfCols) / (T.cps * 16) : (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
     T.rslots = f4 ? 6 : kRawSlots;      // 4-bit path: raw slots are up to 14 KB
-    // in-kernel feature conversion (opt-in: QGTC_TC05_CONV=1; default is the separate prep_b_kernel): needs an expander
-    // group without items (fewer than four stages).  Measured on B200 (4096 x 4096 x 64,
-    // 96 graphs): the GEMM kernel is bound by its ALU / issue slots, so the converters' instructions cost more inside it
-    // (+17 us at 1 bit, +83 us at 8 bits) than prep_b_kernel and its launch gap cost outside (15 / 29 us).
-    static const bool conv_env = [] { const char* e = getenv("QGTC_TC05_CONV"); return e && e[0] == '1'; }();
-    const bool conv_want = conv_env && !pair;
+    // (Converting the features inside this kernel, by an expander group without items, was built and measured on
+    // B200 -- 4096 x 4096 x 64, 96 graphs: +17 us at 1 bit, +83 us at 8 bits per launch against 8-17 us for the
+    // separate prep kernel: the GEMM warps have no issue slots to spare.  Removed)
     while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair, T.rslots, f4).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
@@ -1443,21 +1358,12 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     uint8_t* img = nullptr;
     const int img_problems = b_shared ? 1 : a.count;
     const size_t img_bytes = (((size_t)a.gdk * chunk_img_bytes * img_problems) + 255) & ~(size_t)255;
-    const bool conv = conv_want && !f4 && T.stages < kProducerWarps / T.wpi;    // an idle expander group exists
-    const size_t conv_bytes = conv ? (size_t)(1 + img_problems) * sizeof(unsigned int) : 0;
-    e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes + conv_bytes, st);
+    e = cudaMallocAsync(reinterpret_cast<void**>(&img), img_bytes, st);
     if (e != cudaSuccess) return record_cuda_error(e, "cudaMallocAsync(feature image)");
     T.bimg = img;
-    T.bimg_w = img;
-    T.conv = nullptr;
-    T.conv_images = img_problems;
 
     int rc = QGTC_OK;
-    if (conv) {   // the GEMM kernel's converter warps build the image: only the job ticket and the per-image counters are prepared here
-        T.conv = reinterpret_cast<unsigned int*>(img + img_bytes);
-        e = cudaMemsetAsync(T.conv, 0, conv_bytes, st);
-        if (e != cudaSuccess) rc = record_cuda_error(e, "cudaMemsetAsync(conversion counters)");
-    } else {
+    {
         GemmArgs pa = a;
         pa.count = img_problems;
         long long pgrid = (long long)img_problems * ((a.gdk + kPrepChunks - 1) / kPrepChunks) * (T.NP / 8);
@@ -1503,7 +1409,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = (pair || conv) ? 1 : 2;
+            cfg.numAttrs = pair ? 1 : 2;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (g_time_on && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess) cudaEventRecord(ev0, st);
             e2 = cudaLaunchKernelEx(&cfg, kfn, T, tmap);
