@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Where does the tcgen05 engine's time go?  Runs the batched 4096x4096xN GEMM with individual pipeline
 stages disabled through the library's timing-experiment flag bits (results are then wrong; timing only)."""
+import os
+os.environ.setdefault("QGTC_TC05_DEBUG_KNOBS", "1")   # the library refuses the knob bits otherwise
 import json
 import os
 import sys

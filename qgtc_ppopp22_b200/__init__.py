@@ -11,6 +11,7 @@ There is no CPU fallback: if the native library is missing, importing the ops ra
 from __future__ import annotations
 
 import importlib
+import importlib.abc
 import importlib.util
 import os
 import sys
@@ -43,6 +44,27 @@ def load_extension():
     spec.loader.exec_module(mod)
     sys.modules["QGTC"] = mod
     return mod
+
+
+class _QGTCFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Makes ``import QGTC`` work after ``import qgtc_ppopp22_b200``: the finder
+    answers only for the top-level name ``QGTC`` and loads the in-tree extension lazily, so importing this
+    package never needs the built library (or torch) by itself."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "QGTC":
+            return None
+        return importlib.util.spec_from_loader("QGTC", self)
+
+    def create_module(self, spec):
+        return load_extension()       # raises ImportError when the extension is not built: no CPU fallback
+
+    def exec_module(self, module):
+        pass
+
+
+if not any(isinstance(f, _QGTCFinder) for f in sys.meta_path):
+    sys.meta_path.append(_QGTCFinder())    # appended: a real `QGTC` on sys.path (the reference's own build) still wins
 
 
 def __getattr__(name):

@@ -183,8 +183,23 @@ def bitMM2Bit_batched(x1, x2, count, M, K, N, bit1, bit2, out_bit, out=None, eng
     with torch.cuda.device(x1.device):
         if out is None:
             out = torch.empty((count, wo), dtype=torch.int32, device=x1.device)
+        else:
+            _req_cuda(out, torch.int32, "out")
+            if out.numel() < count * wo:
+                raise QgtcError("out must hold count * %d words (got %d)" % (wo, out.numel()))
         _check(lib().qgtc_bitmm2bit_batched(x1.data_ptr(), s1, x2.data_ptr(), s2, count, M, K, N, bit1, bit2, out_bit,
-                                            out.data_ptr(), wo if out.numel() >= count * wo else 0, engine, flags, _stream()), "bitMM2Bit_batched")
+                                            out.data_ptr(), wo, engine, flags, _stream()), "bitMM2Bit_batched")
+    return out
+
+
+def bitMM2Bit_aliased(x1, x2, count, M, K, N, bit1, bit2, out_bit, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
+    """`count` repetitions of ONE problem in one launch, all writing the same output (out stride 0): the throughput
+    form of QGTC.bitMM2Bit_profile (QGTC_device.cu:403-418, 200 back-to-back launches on the same operands)."""
+    _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2")
+    with torch.cuda.device(x1.device):
+        out = torch.empty(packed_shape(LAYOUT_ROW, out_bit, M, N), dtype=torch.int32, device=x1.device)
+        _check(lib().qgtc_bitmm2bit_batched(x1.data_ptr(), 0, x2.data_ptr(), 0, count, M, K, N, bit1, bit2, out_bit,
+                                            out.data_ptr(), 0, engine, flags, _stream()), "bitMM2Bit_aliased")
     return out
 
 
@@ -207,9 +222,15 @@ def bitMM2Bit_tilemap(x1, x2, tile_map, count, M, K, N, bit2, out_bit, out=None,
     if x1.numel() != count * w1 or x2.numel() not in (w2, count * w2):
         raise QgtcError("tilemap operands must hold `count` well-formed problems")
     s2 = 0 if (count > 1 and x2.numel() == w2) else w2
+    if tile_map.numel() < int(lib().qgtc_tile_bitmap_words(M, K, count)):
+        raise QgtcError("tile_map holds %d words, the problem needs %d" % (tile_map.numel(), int(lib().qgtc_tile_bitmap_words(M, K, count))))
     with torch.cuda.device(x1.device):
         if out is None:
             out = torch.empty((count, wo), dtype=torch.int32, device=x1.device)
+        else:
+            _req_cuda(out, torch.int32, "out")
+            if out.numel() < count * wo:
+                raise QgtcError("out must hold count * %d words (got %d)" % (wo, out.numel()))
         _check(lib().qgtc_bitmm2bit_tilemap(x1.data_ptr(), w1, x2.data_ptr(), s2, tile_map.data_ptr(), count, M, K, N, bit2, out_bit,
                                             out.data_ptr(), wo, engine, flags, _stream()), "bitMM2Bit_tilemap")
     return out
@@ -217,6 +238,8 @@ def bitMM2Bit_tilemap(x1, x2, tile_map, count, M, K, N, bit2, out_bit, out=None,
 
 def bitMM2Int_tilemap(x1, x2, tile_map, M, K, N, bit2, pad_128=False, engine=ENGINE_AUTO, flags=0) -> torch.Tensor:
     _req_cuda(x1, torch.int32, "bit_X1"); _req_cuda(x2, torch.int32, "bit_X2"); _req_cuda(tile_map, torch.int32, "tile_map")
+    if tile_map.numel() < int(lib().qgtc_tile_bitmap_words(M, K, 1)):
+        raise QgtcError("tile_map holds %d words, the problem needs %d" % (tile_map.numel(), int(lib().qgtc_tile_bitmap_words(M, K, 1))))
     with torch.cuda.device(x1.device):
         out = torch.empty((M, N), dtype=torch.float32, device=x1.device)
         _check(lib().qgtc_bitmm2int_tilemap(x1.data_ptr(), x1.numel(), x2.data_ptr(), x2.numel(), tile_map.data_ptr(), M, K, N, bit2,

@@ -52,9 +52,18 @@ static int check_device() {
     return cached_rc;
 }
 
+// flag bits a caller may set; the tcgen05 timing-experiment knobs (0x10000..0x400000, results are wrong by design)
+// are accepted only when QGTC_TC05_DEBUG_KNOBS=1 is set in the environment
+static bool flags_ok(unsigned flags) {
+    const unsigned documented = QGTC_FLAG_NO_ZERO_JUMP | QGTC_FLAG_COL_REF_QUIRK | QGTC_FLAG_TC05_PAIR;
+    if ((flags & ~documented) == 0) return true;
+    static const bool knobs = [] { const char* e = std::getenv("QGTC_TC05_DEBUG_KNOBS"); return e && e[0] == '1'; }();
+    return knobs && (flags & ~(documented | 0x6F0000u)) == 0;
+}
+
 static int fill_gemm_args(GemmArgs& a, const int32_t* x1, size_t x1_words, const int32_t* x2, size_t x2_words,
                           int M, int K, int N, int bit1, int bit2, int out_bit, bool pad128, void* out, unsigned flags) {
-    if (!x1 || !x2 || !out || M <= 0 || K <= 0 || N <= 0) return QGTC_ERR_INVALID_ARG;
+    if (!x1 || !x2 || !out || M <= 0 || K <= 0 || N <= 0 || !flags_ok(flags)) return QGTC_ERR_INVALID_ARG;
     if (!bits_ok(bit1) || !bits_ok(bit2) || !bits_ok(out_bit)) return QGTC_ERR_UNSUPPORTED;
     if (!aligned16(x1) || !aligned16(x2) || !aligned16(out)) return QGTC_ERR_ALIGNMENT;
     if ((long long)p8(M) * s128(K) * 4 * 8 > (1ll << 40) || (long long)p128(N) * s128(K) * 4 * 8 > (1ll << 40)) return QGTC_ERR_UNSUPPORTED;
@@ -76,7 +85,12 @@ static int fill_gemm_args(GemmArgs& a, const int32_t* x1, size_t x1_words, const
 
 static int run_gemm(const GemmArgs& a, int epi, int engine, cudaStream_t st) {
     if (engine == QGTC_ENGINE_TCGEN05) return launch_gemm_tc05(a, epi, st);
-    if (engine == QGTC_ENGINE_AUTO && tc05_supports(a, epi)) return launch_gemm_tc05(a, epi, st);
+    if (engine == QGTC_ENGINE_AUTO && tc05_supports(a, epi)) {
+        // launch_gemm_tc05 can still refuse (tensor-map encoding, shared-memory fit) -- it does so before any work is
+        // enqueued, and the general engine handles every shape
+        const int rc = launch_gemm_tc05(a, epi, st);
+        if (rc != QGTC_ERR_UNSUPPORTED) return rc;
+    }
     if (engine == QGTC_ENGINE_AUTO || engine == QGTC_ENGINE_MMA_SYNC) return launch_gemm_mma(a, epi, st);
     return QGTC_ERR_INVALID_ARG;
 }
@@ -88,20 +102,22 @@ struct Scratch {
     int dev = -1;
 };
 static std::mutex g_scratch_mu;
-static Scratch g_scratch;
+constexpr int kMaxDevices = 64;
+static Scratch g_scratch_by_dev[kMaxDevices];   // one growing buffer per device (a process may drive several GPUs)
 static int scratch_reserve(size_t bytes, void** out) {
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (g_scratch.dev != dev || g_scratch.bytes < bytes) {
-        if (g_scratch.p && g_scratch.dev == dev) cudaFree(g_scratch.p);
-        g_scratch = Scratch{};
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return QGTC_ERR_NO_DEVICE; }
+    Scratch& sc = g_scratch_by_dev[dev];
+    if (sc.bytes < bytes) {
+        if (sc.p) cudaFree(sc.p);     // the current device is `dev`, the one that owns the buffer
+        sc = Scratch{};
         const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
-        const cudaError_t e = cudaMalloc(&g_scratch.p, want);
-        if (e != cudaSuccess) { g_scratch = Scratch{}; return record_cuda_error(e, "cudaMalloc(scratch)"); }
-        g_scratch.bytes = want;
-        g_scratch.dev = dev;
+        const cudaError_t e = cudaMalloc(&sc.p, want);
+        if (e != cudaSuccess) { sc = Scratch{}; return record_cuda_error(e, "cudaMalloc(scratch)"); }
+        sc.bytes = want;
+        sc.dev = dev;
     }
-    *out = g_scratch.p;
+    *out = sc.p;
     return QGTC_OK;
 }
 
@@ -216,7 +232,7 @@ int qgtc_bitmm2bit_batched(const int32_t* x1_dev, size_t x1_stride_words, const 
     const size_t need_o = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
     if (int rc = fill_gemm_args(a, x1_dev, need1, x2_dev, need2, M, K, N, bit1, bit2, out_bit, true, out_dev, flags)) return rc;
     if ((x1_stride_words & 3) || (x2_stride_words & 3) || (out_stride_words & 3)) return QGTC_ERR_ALIGNMENT;
-    if (out_stride_words && out_stride_words < need_o) return QGTC_ERR_SIZE;
+    if (out_stride_words && out_stride_words < need_o) return QGTC_ERR_SIZE;   // 0 = every problem aliases one output (bitMM2Bit_profile)
     if ((x1_stride_words && x1_stride_words < need1) || (x2_stride_words && x2_stride_words < need2)) return QGTC_ERR_SIZE;
     a.count = count;
     a.x1_bstride = x1_stride_words;
@@ -259,8 +275,11 @@ int qgtc_bitmm2bit_tilemap(const int32_t* x1_dev, size_t x1_stride_words, const 
     const size_t need2 = qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N);
     const size_t need_o = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
     if (int rc = fill_gemm_args(a, x1_dev, need1, x2_dev, need2, M, K, N, 1, bit2, out_bit, true, out_dev, flags)) return rc;
+    if (!bitmap_dev) return QGTC_ERR_INVALID_ARG;
     if ((x1_stride_words & 3) || (x2_stride_words & 3) || (out_stride_words & 3)) return QGTC_ERR_ALIGNMENT;
-    if (count > 1 && out_stride_words && out_stride_words < need_o) return QGTC_ERR_SIZE;
+    if (count > 1 && out_stride_words < need_o) return QGTC_ERR_SIZE;       // problems must not share an output
+    if ((count > 1 || x1_stride_words) && x1_stride_words < need1) return QGTC_ERR_SIZE;
+    if (x2_stride_words && x2_stride_words < need2) return QGTC_ERR_SIZE;
     a.count = count;
     a.x1_bstride = x1_stride_words;
     a.x2_bstride = x2_stride_words;

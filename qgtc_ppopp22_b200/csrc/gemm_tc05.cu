@@ -25,6 +25,7 @@
 // 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.  With a precomputed tile bitmap
 // (qgtc_tile_bitmap) all-zero stages are skipped by every role.
 #include <cuda.h>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -1196,7 +1197,8 @@ unsigned int* g_error_flag = nullptr;  // device alias of g_error_flag_host
 unsigned int* g_error_flag_host = nullptr;  // one mapped host word per process: where a watchdog fired (0x80000000 | site)
 // kernel timing (qgtc_debug_tc05_time): cudaEvent pairs around the GEMM kernel launches, read by qgtc_debug_tc05_kernel_times
 bool g_time_on = false;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_time_events;   // guarded by g_time_mu
+std::mutex g_time_mu;
 unsigned long long* g_trace = nullptr;  // clock64 trace buffer, only with QGTC_TC05_TRACE=1
 constexpr size_t kTraceWords = 8 * (size_t)kTraceItems * 8;
 
@@ -1415,6 +1417,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             e2 = cudaLaunchKernelEx(&cfg, kfn, T, tmap);
             if (ev0 && ev1) {
                 cudaEventRecord(ev1, st);
+                std::lock_guard<std::mutex> lk(g_time_mu);
                 g_time_events.emplace_back(ev0, ev1);
             }
             note_launch();
@@ -1456,6 +1459,7 @@ extern "C" unsigned int qgtc_debug_tc05_error_flag() { return g_error_flag_host 
 extern "C" void qgtc_debug_tc05_time(int on) { g_time_on = on != 0; }
 extern "C" int qgtc_debug_tc05_kernel_times(float* dst, int max_n) {
     int n = 0;
+    std::lock_guard<std::mutex> lk(g_time_mu);
     for (auto& pr : g_time_events) {
         float ms = 0.f;
         if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess && n < max_n) dst[n++] = ms;

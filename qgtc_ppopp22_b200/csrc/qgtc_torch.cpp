@@ -158,6 +158,7 @@ torch::Tensor bitMM2Bit_profile(torch::Tensor bit_X1, torch::Tensor bit_X2, cons
 
 // base_cnt only advances counter_global (kernel.h:452), zerojump_cnt only counter (kernel.h:587)
 void add_counts(const torch::Tensor& X1, int M, int K, int N, int bit1, int bit2, bool global_counter) {
+    const c10::cuda::CUDAGuard guard(X1.device());     // the count kernel runs on the tensor's device and its current stream
     auto a = packed_input(X1, "bit_X1");
     uint64_t total = 0, nz = 0;
     check_status(qgtc_tile_counts(a.data_ptr<int32_t>(), (size_t)a.numel(), M, K, N, bit1, bit2, &total, &nz, current_stream()),

@@ -73,3 +73,21 @@ def test_no_oracle_imports_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert "bitplane_oracle" not in src and "c_oracle" not in src and "liboracle" not in src, f
+
+
+def test_import_QGTC_after_package_import_in_fresh_interpreter():
+    """`import qgtc_ppopp22_b200; import QGTC` is the whole switch-over."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import qgtc_ppopp22_b200; import QGTC; "
+            "assert QGTC.__backend__ == 'qgtc_b200' and callable(QGTC.bitMM2Int); print('ok')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_undocumented_flag_bits_are_refused():
+    from qgtc_ppopp22_b200 import capi
+    L = capi.lib()
+    # the tcgen05 timing knobs (0x10000..) produce wrong results by design: refused unless QGTC_TC05_DEBUG_KNOBS=1
+    assert L.qgtc_bitmm2bit(16, 64, 16, 64, 8, 8, 8, 1, 1, 1, 16, 64, 0, 0x10000, None) == 1
+    assert L.qgtc_bitmm2bit(16, 64, 16, 64, 8, 8, 8, 1, 1, 1, 16, 64, 0, 0x8, None) == 1

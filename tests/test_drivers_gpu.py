@@ -97,3 +97,32 @@ def test_gcnconv_qnt_matches_integer_math(oracle):
     hw = oracle.requantize(hq @ W2, ab) & mask
     want = (An @ hw).astype(np.float32)
     assert got.shape == (n, C) and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_arxiv_shaped_chain_matches_oracle(coracle, bits):
+    """One ogbn-arxiv-sized batch (n ~ 2258, D = 128, h = 16, C = 40: BASELINE configs[2]) through the GCN op sequence
+    of main_qgtc.py:146-154 at 4 and 8 bits, every op defined on raw memory, against the C oracle."""
+    import qgtc_ppopp22_b200
+    from qgtc_ppopp22_b200 import main_qgtc as drv
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    n, D, h, ncls, b = 2258, 128, 16, 40, bits
+    rng = np.random.default_rng(100 + bits)
+    A = (rng.random((n, n)) < 0.004).astype(np.float32)
+    X = rng.standard_normal((n, D)).astype(np.float32) * 3
+    dA, dX = torch.from_numpy(A).cuda(), torch.from_numpy(X).cuda()
+    bit_A, bit_X = QGTC.val2bit(dA, 1, False, False), QGTC.val2bit(dX, b, True, False)
+    W = drv.pack_weights(QGTC, D, h, ncls, b, torch.device("cuda"))
+    got = drv.gcn_forward(QGTC, bit_A, bit_X, W, n, D, b).cpu().numpy()
+    o = coracle
+    oW = (o.val2bit(np.ones((D, h), np.float32), b, True, False), o.val2bit(np.ones((h, h), np.float32), b, True, False),
+          o.val2bit(np.ones((h, ncls), np.float32), b, True, True))
+    bA, bX = o.val2bit(A, 1, False, False), o.val2bit(X, b, True, False)
+    assert np.array_equal(bit_A.cpu().numpy().view(np.uint32), bA) and np.array_equal(bit_X.cpu().numpy().view(np.uint32), bX)
+    t = o.bitMM2Bit(bX, oW[0], n, D, h, b, b, b)
+    t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+    t = o.bitMM2Bit(t, oW[1], n, h, h, b, b, b)
+    t = o.bitMM2Bit(bA, t, n, n, h, 1, b, b)
+    t = o.bitMM2Bit(t, oW[2], n, h, ncls, b, b, b)
+    want = o.bitMM2Int(bA, t, n, n, h, 1, b, False)
+    assert np.array_equal(got, want)

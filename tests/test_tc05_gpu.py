@@ -195,3 +195,82 @@ def test_tc05_expansion_modes_agree(mode):
     env = dict(os.environ, QGTC_TC05_FP4="1") if mode == "fp4" else dict(os.environ, QGTC_TC05_AMODE=str(mode), QGTC_TC05_FP4="0")
     r = subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kind::mxf4 operand path (1- and 2-bit features: E2M1 x E2M1 -> f32 accumulators in TMEM).  The reference accumulates
+# in exact int32 (kernel.h:338-342); the f32 accumulation of the tensor core must therefore be exact for every sum the
+# launcher's guard (max_sum < 2^23, gemm_tc05.cu launch_gemm_tc05) admits.  These cases drive the accumulators to
+# their largest values: all-ones adjacency rows, maximal features, K up to the largest the guard admits.
+# ---------------------------------------------------------------------------------------------------------------
+def _max_k_under_f4_guard(b):
+    gdk = (8388608 - 1) // (128 * ((1 << b) - 1))
+    while gdk * 128 * ((1 << b) - 1) >= 8388608:
+        gdk -= 1
+    return gdk * 128
+
+
+@pytest.mark.parametrize("b", [1, 2])
+@pytest.mark.parametrize("K", [4096, 8192, 16384, 65536, "max"])
+@pytest.mark.parametrize("N", [16, 64, 256])
+def test_tc05_f4_exact_at_worst_case_sums(capi, b, K, N):
+    if K == "max":
+        if N != 16:
+            pytest.skip("the largest K is run at N = 16 only (operand size)")
+        K = _max_k_under_f4_guard(b)
+    M = 136                                   # two row tiles, the second one ragged
+    top = (1 << b) - 1
+    A = torch.ones((M, K), device="cuda")
+    da = capi.val2bit(A, 1, False, False)
+    del A
+    # (1) every feature maximal: every accumulator == K * (2^b - 1)
+    X = torch.full((K, N), float(top), device="cuda")
+    got = capi.bitMM2Int(da, capi.val2bit(X, b, True, False), M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05)
+    assert got.shape == (M, N)
+    assert bool((got == float(K * top)).all()), (float(got.min()), float(got.max()), K * top)
+    # (2) random features: every row of the result == the exact column sums (odd and even low bits on top of large sums)
+    g = torch.Generator(device="cuda").manual_seed(K % 9973 + N + b)
+    Xr = torch.randint(0, top + 1, (K, N), device="cuda", generator=g)
+    want = Xr.sum(dim=0, dtype=torch.int64)
+    dx = capi.val2bit(Xr.float(), b, True, False)
+    got = capi.bitMM2Int(da, dx, M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05)
+    assert torch.equal(got.to(torch.int64), want.view(1, N).expand(M, N))
+    # (3) the requantizing epilogue on the same accumulators agrees with the integer engine (exact int32)
+    if K <= 65536:
+        ob = 8
+        bits_tc = capi.bitMM2Bit(da, dx, M, K, N, 1, b, ob, engine=capi.ENGINE_TCGEN05)
+        bits_mma = capi.bitMM2Bit(da, dx, M, K, N, 1, b, ob, engine=capi.ENGINE_MMA_SYNC)
+        assert torch.equal(bits_tc, bits_mma)
+
+
+def test_tc05_f4_dense_16384_vs_c_oracle(capi, coracle):
+    """BASELINE configs[4]'s largest adjacency, dense (Bernoulli 0.9 rows sum to ~44K at 2 bits), against the C oracle."""
+    M = K = 16384
+    N, b = 64, 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.rand((M, K), device="cuda", generator=g) < 0.9).float()
+    X = torch.randint(0, 4, (K, N), device="cuda", generator=g).float()
+    da, dx = capi.val2bit(A, 1, False, False), capi.val2bit(X, b, True, False)
+    del A
+    got = capi.bitMM2Int(da, dx, M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05).cpu().numpy()
+    want = coracle.bitMM2Int(host_u32(da), host_u32(dx), M, K, N, 1, b, True)
+    assert np.array_equal(got, want)
+    gb = capi.bitMM2Bit(da, dx, M, K, N, 1, b, 8, engine=capi.ENGINE_TCGEN05)
+    assert np.array_equal(host_u32(gb), coracle.bitMM2Bit(host_u32(da), host_u32(dx), M, K, N, 1, b, 8))
+
+
+# BASELINE configs[1], the whole Fig. 8a grid with random inputs (2_7c_QGTC_GEMM_INT8.py shapes), tcgen05 engine
+@pytest.mark.parametrize("b", [1, 2, 4, 8])
+@pytest.mark.parametrize("N", [16, 32, 64])
+@pytest.mark.parametrize("M", [1024, 2048, 4096])
+def test_tc05_fig8a_grid_random(capi, coracle, M, N, b):
+    K = M
+    g = torch.Generator(device="cuda").manual_seed(M + 13 * N + b)
+    A = (torch.rand((M, K), device="cuda", generator=g) < 0.5).float()
+    X = torch.randint(0, 1 << b, (K, N), device="cuda", generator=g).float()
+    da, dx = capi.val2bit(A, 1, False, False), capi.val2bit(X, b, True, False)
+    ha, hx = host_u32(da), host_u32(dx)
+    got = capi.bitMM2Bit(da, dx, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
+    assert np.array_equal(host_u32(got), coracle.bitMM2Bit(ha, hx, M, K, N, 1, b, b))
+    gi = capi.bitMM2Int(da, dx, M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05)
+    assert np.array_equal(gi.cpu().numpy(), coracle.bitMM2Int(ha, hx, M, K, N, 1, b, True))
