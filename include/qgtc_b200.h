@@ -53,7 +53,8 @@ typedef enum qgtc_layout { QGTC_LAYOUT_ROW = 0, QGTC_LAYOUT_COL128 = 1, QGTC_LAY
 typedef enum qgtc_gemm_engine {
     QGTC_ENGINE_AUTO = 0,    /* library picks (tcgen05 when the shape qualifies, else mma.sync) */
     QGTC_ENGINE_MMA_SYNC = 1,/* legacy warp-level mma.sync.m16n8k32.u8 on re-assembled planes   */
-    QGTC_ENGINE_TCGEN05 = 2  /* tcgen05.mma kind::i8, TMEM accumulators                         */
+    QGTC_ENGINE_TCGEN05 = 2, /* tcgen05.mma, TMEM accumulators, TMA-fed uniform batches (1-bit X1 only) */
+    QGTC_ENGINE_GROUPED = 3  /* tcgen05.mma, grouped variable-shape engine: any bit1, in-kernel operand conversion */
 } qgtc_gemm_engine;
 
 /* flags for the GEMM entry points */
@@ -153,6 +154,29 @@ int qgtc_bitmm2bit_host(const int32_t* x1_host, size_t x1_words, const int32_t* 
 int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, const int32_t* x2_host, size_t x2_stride_words,
                                 int count, int M, int K, int N, int bit1, int bit2, int out_bit,
                                 int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream);
+
+/* Grouped bit-GEMM: ONE launch for `count` independent problems that share N, the bit widths and the kind of result but
+ * have their own M, K, operands and output -- e.g. one op of the Cluster-GCN / batched-GIN forward for all batches of a
+ * rank (the per-batch loop of main_qgtc.py:113-154 turned inside out: 6 launches per epoch instead of 6 x batches).
+ * Results are identical to `count` calls of qgtc_bitmm2bit (QGTC_GROUP_BITS_ROW; QGTC_device.cu:211-266),
+ * qgtc_bitmm2int (QGTC_GROUP_FLOAT; QGTC_device.cu:495-542) or qgtc_bitmm2bit_col (QGTC_GROUP_BITS_COL;
+ * QGTC_device.cu:441-489, intended semantics): same raw-memory indexing, same zero-extension rule.
+ * `problems_host` is an array in HOST memory (read before the call returns; its pointers are device pointers).
+ * out_size: words of the packed result buffer, or float elements for QGTC_GROUP_FLOAT.  tile_bitmap_dev (optional, 1-bit X1
+ * only): the problem's qgtc_tile_bitmap; all-zero tiles are then skipped.  pad128 is used by QGTC_GROUP_FLOAT only. */
+typedef struct qgtc_group_problem {
+    const int32_t* x1_dev;
+    size_t x1_words;
+    const int32_t* x2_dev;
+    size_t x2_words;
+    void* out_dev;
+    size_t out_size;
+    const uint32_t* tile_bitmap_dev;
+    int32_t M, K;
+} qgtc_group_problem;
+typedef enum qgtc_group_kind { QGTC_GROUP_BITS_ROW = 0, QGTC_GROUP_FLOAT = 1, QGTC_GROUP_BITS_COL = 2 } qgtc_group_kind;
+int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,
+                       int kind, int pad128, int engine, unsigned flags, void* stream);
 
 /* Number of kernels this library has launched from the calling process (bench.py gpu_launches). */
 uint64_t qgtc_launch_count(void);

@@ -39,9 +39,9 @@ def bench(engine, n, N, b, reps=20):
 
 if __name__ == "__main__":
     for n in (759, 1283, 2258, 4096, 8192):
-        for N in (16, 64, 128):
+        for N in (16, 64):
             r = {"n": n, "N": N, "bits": 2, "gop": round(2.0 * n * n * N / 1e9, 3)}
-            for name, e in (("mma", capi.ENGINE_MMA_SYNC), ("tcgen05", capi.ENGINE_TCGEN05)):
+            for name, e in (("mma", capi.ENGINE_MMA_SYNC), ("tcgen05", capi.ENGINE_TCGEN05), ("grouped", capi.ENGINE_GROUPED), ("auto", capi.ENGINE_AUTO)):
                 try:
                     r[name + "_us"] = round(bench(e, n, N, 2), 2)
                 except Exception as ex:

@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 INCLUDE = os.path.join(ROOT, "include")
 
-CUDA_SOURCES = ["abi.cu", "pack.cu", "gemm_mma.cu", "gemm_tc05.cu"]
+CUDA_SOURCES = ["abi.cu", "pack.cu", "gemm_mma.cu", "gemm_tc05.cu", "gemm_grp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -14,7 +14,8 @@ import torch
 
 from . import lib_dir
 
-ENGINE_AUTO, ENGINE_MMA_SYNC, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_MMA_SYNC, ENGINE_TCGEN05, ENGINE_GROUPED = 0, 1, 2, 3
+GROUP_BITS_ROW, GROUP_FLOAT, GROUP_BITS_COL = 0, 1, 2
 FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK, FLAG_TC05_PAIR = 0x1, 0x2, 0x4
 LAYOUT_ROW, LAYOUT_COL128, LAYOUT_COL8 = 0, 1, 2
 
@@ -24,8 +25,15 @@ SYMBOLS = [
     "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
-    "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit",
+    "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit", "qgtc_bitmm_grouped",
 ]
+
+
+class GroupProblem(ctypes.Structure):
+    """qgtc_group_problem (include/qgtc_b200.h)."""
+    _fields_ = [("x1_dev", ctypes.c_void_p), ("x1_words", ctypes.c_size_t), ("x2_dev", ctypes.c_void_p), ("x2_words", ctypes.c_size_t),
+                ("out_dev", ctypes.c_void_p), ("out_size", ctypes.c_size_t), ("tile_bitmap_dev", ctypes.c_void_p),
+                ("M", ctypes.c_int32), ("K", ctypes.c_int32)]
 
 _LIB = None
 
@@ -71,6 +79,7 @@ def lib() -> ctypes.CDLL:
         L.qgtc_tile_bitmap.argtypes = [vp, sz, sz, i, i, i, vp, sz, vp]
         L.qgtc_bitmm2bit_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2int_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm_grouped.argtypes = [c.POINTER(GroupProblem), i, i, i, i, i, i, i, i, c.c_uint, vp]
         _LIB = L
     return _LIB
 
@@ -284,3 +293,42 @@ def edges2bit(rows: torch.Tensor, cols: torch.Tensor, H: int, W: int) -> torch.T
         out = torch.empty(packed_shape(LAYOUT_ROW, 1, H, W), dtype=torch.int32, device=rows.device)
         _check(lib().qgtc_edges2bit(rows.data_ptr(), cols.data_ptr(), rows.numel(), H, W, out.data_ptr(), out.numel(), _stream()), "edges2bit")
     return out
+
+
+def bitmm_grouped(x1s, x2s, Ms, Ks, N, bit1, bit2, out_bit, kind=GROUP_BITS_ROW, pad_128=False, tile_maps=None, outs=None,
+                  engine=ENGINE_AUTO, flags=0):
+    """One launch for len(x1s) independent problems sharing N and the bit widths (qgtc_bitmm_grouped): problem i is
+    x1s[i] (R(bit1, Ms[i], Ks[i]) raw words) x x2s[i] (C(bit2, Ks[i], N) raw words).  Results equal bitMM2Bit /
+    bitMM2Int / bitMM2Bit_col of each problem.  Returns the list of outputs (views of one allocation unless `outs` is given)."""
+    count = len(x1s)
+    if not (count == len(x2s) == len(Ms) == len(Ks)) or count == 0:
+        raise QgtcError("bitmm_grouped: operand lists must be non-empty and of equal length")
+    dev = x1s[0].device
+    arr = (GroupProblem * count)()
+    if kind == GROUP_FLOAT:
+        sizes = [int(m) * N for m in Ms]
+        shapes = [(int(m), N) for m in Ms]
+        dtype = torch.float32
+    else:
+        layout = LAYOUT_ROW if kind == GROUP_BITS_ROW else LAYOUT_COL128
+        shapes = [packed_shape(layout, out_bit, int(m), N) for m in Ms]
+        sizes = [a * b for a, b in shapes]
+        dtype = torch.int32
+    with torch.cuda.device(dev):
+        if outs is None:
+            offs, total = [], 0
+            for sz_ in sizes:
+                offs.append(total)
+                total += (sz_ + 3) & ~3                 # keep every problem's output 16-byte aligned
+            flat = torch.empty((total,), dtype=dtype, device=dev)
+            outs = [flat[o:o + sz_].view(shp) for o, sz_, shp in zip(offs, sizes, shapes)]
+        for k in range(count):
+            a, b, o = x1s[k], x2s[k], outs[k]
+            _req_cuda(a, torch.int32, "bit_X1[%d]" % k); _req_cuda(b, torch.int32, "bit_X2[%d]" % k); _req_cuda(o, dtype, "out[%d]" % k)
+            p = arr[k]
+            p.x1_dev, p.x1_words, p.x2_dev, p.x2_words = a.data_ptr(), a.numel(), b.data_ptr(), b.numel()
+            p.out_dev, p.out_size = o.data_ptr(), o.numel()
+            p.tile_bitmap_dev = tile_maps[k].data_ptr() if tile_maps is not None and tile_maps[k] is not None else None
+            p.M, p.K = int(Ms[k]), int(Ks[k])
+        _check(lib().qgtc_bitmm_grouped(arr, count, N, bit1, bit2, out_bit, kind, int(bool(pad_128)), engine, flags, _stream()), "bitmm_grouped")
+    return outs

@@ -119,7 +119,7 @@ class ClusterIter:
 
     def __init__(self, dn, g: SyntheticGraph, psize, batch_size, seed_nid=None, use_pp=False, regular=False,
                  bit_width=2, run_GIN=False, device=None, batch_ids=None, keep_on_cpu=False, ops=None, par_li=None,
-                 from_edges=False):
+                 from_edges=False, tile_bitmaps=False):
         self.g = g
         self.psize = psize
         self.batch_size = batch_size
@@ -133,6 +133,7 @@ class ClusterIter:
             self.par_li = list(par_li)                    # already shuffled (multi-rank runs share one order)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.cTensor_li, self.cluster_param_li, self.batch_nodes = [], [], []
+        self.tile_maps, self._tile_stats = [], [0, 0]      # per batch: qgtc_tile_bitmap of bit_A (zero-tile jumping); [non-zero, total] tiles
         self.batch_ids = list(range(self.max)) if batch_ids is None else list(batch_ids)
         if ops is None:
             import qgtc_ppopp22_b200
@@ -171,11 +172,22 @@ class ClusterIter:
                 A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
                 bit_A = ops.val2bit(A, 1, False, False)
             bit_X = ops.val2bit(X, self.bit_width, True, False)
+            if tile_bitmaps:
+                # built once, when the batch is packed (the reference re-tests every 8 x 128 tile inside every GEMM, kernel.h:574-591)
+                from . import capi
+                bm = capi.tile_bitmap(bit_A, n, n).view(-1)
+                self.tile_maps.append(bm)
+                self._tile_stats[0] += int(sum(bin(w & 0xFFFFFFFF).count("1") for w in bm.cpu().tolist()))
+                self._tile_stats[1] += ((n + 7) // 8 * 8 + 127) // 128 * ((n + 127) // 128)
             if keep_on_cpu:
                 bit_A, bit_X = bit_A.cpu(), bit_X.cpu()
             self.cTensor_li.append(ClusterTensor(bit_A, bit_X))
             self.cluster_param_li.append((n, n, n, int(X.size(1))))
             del A
+
+    def nonzero_tile_fraction(self) -> float:
+        """processed / total 128 x 128-bit adjacency tiles over this iterator's batches (what parse_counter.py:16 reports)."""
+        return self._tile_stats[0] / self._tile_stats[1] if self._tile_stats[1] else 1.0
 
     def __len__(self):
         return len(self.cTensor_li)

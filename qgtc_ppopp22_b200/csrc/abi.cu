@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "gemm_common.cuh"
 
@@ -20,6 +21,18 @@ int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int 
 int launch_gemm_mma(const GemmArgs& a, int epi, cudaStream_t st);
 int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st);   // QGTC_ERR_UNSUPPORTED when the shape does not qualify
 bool tc05_supports(const GemmArgs& a, int epi);
+// grouped tcgen05 engine (gemm_grp.cu): `count` problems of different M, K in one launch
+struct GroupedProblemHost {
+    const uint32_t* x1;
+    const uint32_t* x2;
+    void* out;
+    const uint32_t* bitmap;
+    unsigned long long x1_words, x2_words;
+    int M, K;
+};
+bool grp_supports(int N, int bit1, int bit2, int epi);
+int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int bit1, int bit2, int out_bit, int epi, int pad128,
+                        unsigned flags, cudaStream_t st);
 
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_cuda_err[256] = "";
@@ -83,8 +96,31 @@ static int fill_gemm_args(GemmArgs& a, const int32_t* x1, size_t x1_words, const
     return QGTC_OK;
 }
 
+// one problem (or a uniform batch that the batch engine refused) on the grouped engine
+static int run_grouped_single(const GemmArgs& a, int epi, cudaStream_t st) {
+    if (a.count != 1) return QGTC_ERR_UNSUPPORTED;
+    GroupedProblemHost h{a.x1, a.x2, a.out, a.tile_bitmap, a.x1_words, a.x2_words, a.M, a.K};
+    const int pad128 = a.w_offset == (unsigned long long)a.gdk * 4 * p128(a.N) ? 1 : 0;
+    return launch_gemm_grouped(&h, 1, a.N, a.bit1, a.bit2, a.out_bit, epi, pad128, a.flags, st);
+}
+
+// QGTC_ENGINE_AUTO, single problems: the batch engine (gemm_tc05.cu: TMA-fed, feature image built by a separate prep
+// kernel, 4-bit operand path) wins on large problems, the grouped engine (one launch, in-kernel conversion) on small ones
+static double auto_batch_engine_min_ops() {
+    static const double v = [] { const char* e = std::getenv("QGTC_AUTO_BATCH_MIN_OPS"); return e ? std::atof(e) : 6.0e9; }();
+    return v;
+}
+
 static int run_gemm(const GemmArgs& a, int epi, int engine, cudaStream_t st) {
     if (engine == QGTC_ENGINE_TCGEN05) return launch_gemm_tc05(a, epi, st);
+    if (engine == QGTC_ENGINE_GROUPED) return run_grouped_single(a, epi, st);
+    if (engine == QGTC_ENGINE_AUTO && a.count == 1 && grp_supports(a.N, a.bit1, a.bit2, epi)) {
+        const double ops = 2.0 * a.M * (double)a.K * a.N;
+        if (!(tc05_supports(a, epi) && ops >= auto_batch_engine_min_ops())) {
+            const int rc = run_grouped_single(a, epi, st);
+            if (rc != QGTC_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (engine == QGTC_ENGINE_AUTO && tc05_supports(a, epi)) {
         // launch_gemm_tc05 can still refuse (tensor-map encoding, shared-memory fit) -- it does so before any work is
         // enqueued, and the general engine handles every shape
@@ -204,10 +240,14 @@ int qgtc_bitmm2bit_col(const int32_t* x1_dev, size_t x1_words, const int32_t* x2
     const size_t need = qgtc_packed_words(QGTC_LAYOUT_COL128, out_bit, M, N);
     if (out_words < need) return QGTC_ERR_SIZE;
     if (int rc = check_device()) return rc;
+    if (!(flags & QGTC_FLAG_COL_REF_QUIRK) && engine != QGTC_ENGINE_MMA_SYNC) {
+        // intended semantics: the grouped tcgen05 engine writes every word of the column-major image itself
+        const int rc = run_grouped_single(a, kEpiBitsCol, (cudaStream_t)stream);
+        if (rc != QGTC_ERR_UNSUPPORTED || engine == QGTC_ENGINE_GROUPED || engine == QGTC_ENGINE_TCGEN05) return rc;
+    }
     // the column-major image has pad words no tile owns: clear it first (off the benchmark path)
     const cudaError_t e = cudaMemsetAsync(out_dev, 0, need * sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(bitmm2bit_col)");
-    (void)engine;  // only the general engine implements the column-major epilogues
     return launch_gemm_mma(a, (flags & QGTC_FLAG_COL_REF_QUIRK) ? kEpiBitsColQuirk : kEpiBitsCol, (cudaStream_t)stream);
 }
 
@@ -426,6 +466,61 @@ int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(s_up);
     if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "sync(bitmm2bit_host_batched)");
     return rc;
+}
+
+int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,
+                       int kind, int pad128, int engine, unsigned flags, void* stream) {
+    if (!problems_host || count <= 0 || N <= 0) return QGTC_ERR_INVALID_ARG;
+    if (kind != QGTC_GROUP_BITS_ROW && kind != QGTC_GROUP_FLOAT && kind != QGTC_GROUP_BITS_COL) return QGTC_ERR_INVALID_ARG;
+    if (!bits_ok(bit1) || !bits_ok(bit2) || (kind != QGTC_GROUP_FLOAT && !bits_ok(out_bit))) return QGTC_ERR_UNSUPPORTED;
+    if (!flags_ok(flags)) return QGTC_ERR_INVALID_ARG;
+    if (kind == QGTC_GROUP_FLOAT) out_bit = 1;
+    if (kind != QGTC_GROUP_FLOAT) pad128 = 1;          // bitMM2Bit / bitMM2Bit_col always read X2 with the C128 plane stride (kernel.h:266)
+    cudaStream_t st = (cudaStream_t)stream;
+    const int epi = kind == QGTC_GROUP_BITS_ROW ? kEpiBitsRow : (kind == QGTC_GROUP_FLOAT ? kEpiFloat : kEpiBitsCol);
+    // validate every problem before anything is enqueued
+    for (int i = 0; i < count; ++i) {
+        const qgtc_group_problem& p = problems_host[i];
+        if (!p.x1_dev || !p.x2_dev || !p.out_dev || p.M <= 0 || p.K <= 0) return QGTC_ERR_INVALID_ARG;
+        if (!aligned16(p.x1_dev) || !aligned16(p.x2_dev) || !aligned16(p.out_dev)) return QGTC_ERR_ALIGNMENT;
+        if ((long long)p8(p.M) * s128(p.K) * 4 * 8 > (1ll << 40) || (long long)p128(N) * s128(p.K) * 4 * 8 > (1ll << 40)) return QGTC_ERR_UNSUPPORTED;
+        const size_t need = kind == QGTC_GROUP_FLOAT ? (size_t)p.M * N
+                                                     : qgtc_packed_words(kind == QGTC_GROUP_BITS_ROW ? QGTC_LAYOUT_ROW : QGTC_LAYOUT_COL128, out_bit, p.M, N);
+        if (p.out_size < need) return QGTC_ERR_SIZE;
+    }
+    if (int rc = check_device()) return rc;
+    const bool quirk = kind == QGTC_GROUP_BITS_COL && (flags & QGTC_FLAG_COL_REF_QUIRK);
+    if (!quirk && engine != QGTC_ENGINE_MMA_SYNC && grp_supports(N, bit1, bit2, epi)) {
+        static thread_local std::vector<GroupedProblemHost> v;
+        v.resize((size_t)count);
+        for (int i = 0; i < count; ++i) {
+            const qgtc_group_problem& p = problems_host[i];
+            v[(size_t)i] = GroupedProblemHost{reinterpret_cast<const uint32_t*>(p.x1_dev), reinterpret_cast<const uint32_t*>(p.x2_dev), p.out_dev,
+                                              p.tile_bitmap_dev, (unsigned long long)p.x1_words, (unsigned long long)p.x2_words, p.M, p.K};
+        }
+        const int rc = launch_gemm_grouped(v.data(), count, N, bit1, bit2, out_bit, epi, pad128, flags, st);
+        if (rc != QGTC_ERR_UNSUPPORTED) return rc;
+    }
+    if (engine == QGTC_ENGINE_GROUPED) return QGTC_ERR_UNSUPPORTED;
+    // fallback: the same problems one call each (identical results)
+    for (int i = 0; i < count; ++i) {
+        const qgtc_group_problem& p = problems_host[i];
+        int rc;
+        if (kind == QGTC_GROUP_BITS_ROW)
+            rc = p.tile_bitmap_dev && bit1 == 1
+                     ? qgtc_bitmm2bit_tilemap(p.x1_dev, 0, p.x2_dev, 0, p.tile_bitmap_dev, 1, p.M, p.K, N, bit2, out_bit,
+                                              reinterpret_cast<int32_t*>(p.out_dev), 0, engine, flags, stream)
+                     : qgtc_bitmm2bit(p.x1_dev, p.x1_words, p.x2_dev, p.x2_words, p.M, p.K, N, bit1, bit2, out_bit,
+                                      reinterpret_cast<int32_t*>(p.out_dev), p.out_size, engine, flags, stream);
+        else if (kind == QGTC_GROUP_FLOAT)
+            rc = qgtc_bitmm2int(p.x1_dev, p.x1_words, p.x2_dev, p.x2_words, p.M, p.K, N, bit1, bit2, pad128,
+                                reinterpret_cast<float*>(p.out_dev), p.out_size, engine, flags, stream);
+        else
+            rc = qgtc_bitmm2bit_col(p.x1_dev, p.x1_words, p.x2_dev, p.x2_words, p.M, p.K, N, bit1, bit2, out_bit,
+                                    reinterpret_cast<int32_t*>(p.out_dev), p.out_size, engine, flags, stream);
+        if (rc != QGTC_OK) return rc;
+    }
+    return QGTC_OK;
 }
 
 uint64_t qgtc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

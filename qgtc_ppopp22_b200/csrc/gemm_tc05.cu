@@ -865,6 +865,16 @@ constexpr size_t kTraceWords = 8 * (size_t)kTraceItems * 8;
 
 }  // namespace
 
+// the watchdog word of the tcgen05 engines (mapped host memory, so the code survives the trap that follows it); null on failure
+unsigned int* tc05_error_flag_device() {
+    if (!g_error_flag) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_error_flag_host), sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *g_error_flag_host = 0u;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_error_flag), g_error_flag_host, 0) != cudaSuccess) { cudaGetLastError(); g_error_flag = nullptr; }
+    }
+    return g_error_flag;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "qgtc_b200.h"
 
@@ -47,6 +48,7 @@ int engine_from_env() {
         if (!s) return (int)QGTC_ENGINE_AUTO;
         if (!std::strcmp(s, "mma")) return (int)QGTC_ENGINE_MMA_SYNC;
         if (!std::strcmp(s, "tcgen05")) return (int)QGTC_ENGINE_TCGEN05;
+        if (!std::strcmp(s, "grouped")) return (int)QGTC_ENGINE_GROUPED;
         return (int)QGTC_ENGINE_AUTO;
     }();
     return e;
@@ -217,6 +219,100 @@ torch::Tensor bitMM2Int(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1
     return out;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Extensions beyond the reference's eight functions (keyword arguments allowed here): the grouped launch -- one op of the
+// forward for ALL batches in one kernel (include/qgtc_b200.h: qgtc_bitmm_grouped) -- the tile bitmap for zero-tile jumping
+// and batch construction from an edge list.
+// ---------------------------------------------------------------------------------------------------------------------
+std::vector<torch::Tensor> grouped_impl(const std::vector<torch::Tensor>& X1s, const std::vector<torch::Tensor>& X2s,
+                                        const std::vector<int64_t>& Ms, const std::vector<int64_t>& Ks, int N, int bit1, int bit2,
+                                        int out_bit, int kind, bool pad_128, const std::vector<torch::Tensor>& tile_maps, const char* op) {
+    const size_t count = X1s.size();
+    TORCH_CHECK(count > 0 && X2s.size() == count && Ms.size() == count && Ks.size() == count, op, ": operand lists must be non-empty and of equal length");
+    TORCH_CHECK(tile_maps.empty() || tile_maps.size() == count, op, ": tile_maps must be empty or hold one bitmap per problem");
+    TORCH_CHECK(N > 0, "dimensions must be positive");
+    const c10::cuda::CUDAGuard guard(X1s[0].device());
+    std::vector<torch::Tensor> keep;          // re-aligned copies (rare) must outlive the launch call
+    std::vector<qgtc_group_problem> probs(count);
+    std::vector<int64_t> offs(count), sizes(count), rows(count), cols(count);
+    int64_t total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        TORCH_CHECK(Ms[i] > 0 && Ks[i] > 0, "dimensions must be positive");
+        if (kind == QGTC_GROUP_FLOAT) { rows[i] = Ms[i]; cols[i] = N; }
+        else qgtc_packed_shape(kind == QGTC_GROUP_BITS_ROW ? QGTC_LAYOUT_ROW : QGTC_LAYOUT_COL128, out_bit, (int)Ms[i], N, &rows[i], &cols[i]);
+        sizes[i] = rows[i] * cols[i];
+        offs[i] = total;
+        total += (sizes[i] + 3) & ~(int64_t)3;          // every problem's output stays 16-byte aligned
+    }
+    auto flat = torch::empty({total}, X1s[0].options().dtype(kind == QGTC_GROUP_FLOAT ? torch::kFloat32 : torch::kInt32));
+    std::vector<torch::Tensor> outs(count);
+    for (size_t i = 0; i < count; ++i) {
+        CHECK_INPUT(X1s[i]);
+        CHECK_INPUT(X2s[i]);
+        TORCH_CHECK(X1s[i].device() == X1s[0].device() && X2s[i].device() == X1s[0].device(), op, ": all operands must live on one device");
+        keep.push_back(packed_input(X1s[i], "bit_X1"));
+        keep.push_back(packed_input(X2s[i], "bit_X2"));
+        const torch::Tensor &a = keep[keep.size() - 2], &b = keep[keep.size() - 1];
+        outs[i] = flat.narrow(0, offs[i], sizes[i]).view({rows[i], cols[i]});
+        qgtc_group_problem& p = probs[i];
+        p.x1_dev = a.data_ptr<int32_t>();
+        p.x1_words = (size_t)a.numel();
+        p.x2_dev = b.data_ptr<int32_t>();
+        p.x2_words = (size_t)b.numel();
+        p.out_dev = outs[i].data_ptr();
+        p.out_size = (size_t)sizes[i];
+        p.tile_bitmap_dev = nullptr;
+        if (!tile_maps.empty() && tile_maps[i].defined() && tile_maps[i].numel() > 0) {
+            TORCH_CHECK(tile_maps[i].is_cuda() && tile_maps[i].scalar_type() == torch::kInt32 && tile_maps[i].is_contiguous(), "tile_map must be a contiguous int32 CUDA tensor");
+            TORCH_CHECK((size_t)tile_maps[i].numel() >= qgtc_tile_bitmap_words((int)Ms[i], (int)Ks[i], 1), "tile_map too small for its problem");
+            p.tile_bitmap_dev = reinterpret_cast<const uint32_t*>(tile_maps[i].data_ptr<int32_t>());
+        }
+        p.M = (int32_t)Ms[i];
+        p.K = (int32_t)Ks[i];
+    }
+    check_status(qgtc_bitmm_grouped(probs.data(), (int)count, N, bit1, bit2, out_bit, kind, pad_128 ? 1 : 0, engine_from_env(), flags_from_env(),
+                                    current_stream()), op);
+    return outs;
+}
+
+std::vector<torch::Tensor> bitMM2Bit_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
+                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, int out_bit, std::vector<torch::Tensor> tile_maps) {
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_ROW, true, tile_maps, "bitMM2Bit_grouped");
+}
+std::vector<torch::Tensor> bitMM2Bit_col_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
+                                                 std::vector<int64_t> Ks, int N, int bit1, int bit2, int out_bit) {
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_COL, true, {}, "bitMM2Bit_col_grouped");
+}
+std::vector<torch::Tensor> bitMM2Int_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
+                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, bool pad_128, std::vector<torch::Tensor> tile_maps) {
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, 1, QGTC_GROUP_FLOAT, pad_128, tile_maps, "bitMM2Int_grouped");
+}
+
+torch::Tensor tile_bitmap(torch::Tensor bit_X1, const int M, const int K) {
+    CHECK_INPUT(bit_X1);
+    const c10::cuda::CUDAGuard guard(bit_X1.device());
+    auto a = packed_input(bit_X1, "bit_X1");
+    TORCH_CHECK(M > 0 && K > 0, "dimensions must be positive");
+    const size_t words = qgtc_tile_bitmap_words(M, K, 1);
+    auto bm = torch::empty({(int64_t)words}, bit_X1.options().dtype(torch::kInt32));
+    check_status(qgtc_tile_bitmap(a.data_ptr<int32_t>(), (size_t)a.numel(), 0, M, K, 1, reinterpret_cast<uint32_t*>(bm.data_ptr<int32_t>()), words,
+                                  current_stream()), "tile_bitmap");
+    return bm;
+}
+
+torch::Tensor edges2bit(torch::Tensor rows, torch::Tensor cols, const int H, const int W) {
+    CHECK_INPUT(rows);
+    CHECK_INPUT(cols);
+    TORCH_CHECK(rows.scalar_type() == torch::kInt32 && cols.scalar_type() == torch::kInt32 && rows.numel() == cols.numel(), "rows / cols must be int32 tensors of equal length");
+    const c10::cuda::CUDAGuard guard(rows.device());
+    int64_t r = 0, c = 0;
+    qgtc_packed_shape(QGTC_LAYOUT_ROW, 1, H, W, &r, &c);
+    auto out = torch::empty({r, c}, rows.options().dtype(torch::kInt32));
+    check_status(qgtc_edges2bit(rows.data_ptr<int32_t>(), cols.data_ptr<int32_t>(), (size_t)rows.numel(), H, W, out.data_ptr<int32_t>(), (size_t)out.numel(),
+                                current_stream()), "edges2bit");
+    return out;
+}
+
 }  // namespace
 
 // Same names, order and docstrings as the reference binding (QGTC_host.cpp:259-271); no py::arg,
@@ -230,5 +326,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("bitMM2Bit_zerojump_cnt", &bitMM2Bit_zerojump_cnt, "QGTC [ bit_A x bit_B --> bit_C ] forward (CUDA) zero jump count");
     m.def("bitMM2Bit_col", &bitMM2Bit_col, "QGTC [ bit_A x bit_B --> bit_C (column major) ] forward (CUDA)");
     m.def("bitMM2Int", &bitMM2Int, "QGTC [ bit_A x bit_B --> float32 ] forward (CUDA)");
+    // extensions (not in the reference): grouped launches, tile bitmap, edge-list packing
+    namespace py = pybind11;
+    m.def("bitMM2Bit_grouped", &bitMM2Bit_grouped, "one launch: bitMM2Bit of every problem of a list (same N and bit widths)", py::arg("X1s"),
+          py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"),
+          py::arg("tile_maps") = std::vector<torch::Tensor>());
+    m.def("bitMM2Bit_col_grouped", &bitMM2Bit_col_grouped, "one launch: bitMM2Bit_col (column-major output) of every problem of a list", py::arg("X1s"),
+          py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"));
+    m.def("bitMM2Int_grouped", &bitMM2Int_grouped, "one launch: bitMM2Int of every problem of a list (same N and bit widths)", py::arg("X1s"),
+          py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("pad_128"),
+          py::arg("tile_maps") = std::vector<torch::Tensor>());
+    m.def("tile_bitmap", &tile_bitmap, "non-zero 128 x 128-bit tile bitmap of a packed 1-bit adjacency (zero-tile jumping)");
+    m.def("edges2bit", &edges2bit, "packed 1-bit adjacency R(1,H,W) from int32 edge endpoints (no dense fp32 intermediate)");
     m.attr("__backend__") = "qgtc_b200";
 }

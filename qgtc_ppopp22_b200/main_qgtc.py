@@ -45,6 +45,12 @@ def build_parser():
     p.add_argument("--cuda-graph", action="store_true", help="capture one epoch in a CUDA graph and replay it")
     p.add_argument("--cpu-baseline", action="store_true", help="also time the torch restatement of the DGL model on the host")
     p.add_argument("--streams", type=int, default=1, help="run independent batches on this many CUDA streams (they share nothing)")
+    p.add_argument("--grouped", action="store_true",
+                   help="issue the epoch op-major: ONE grouped launch per op over all of this rank's batches (6 launches per epoch)")
+    p.add_argument("--tile-bitmap", choices=["auto", "on", "off"], default="auto",
+                   help="--grouped: pass the batches' tile bitmaps (zero-tile jumping); auto = when under half of the tiles are non-zero")
+    p.add_argument("--dense-pack", action="store_true", help="build batches through the dense fp32 n x n adjacency as sampler.py:87-89 does "
+                                                              "(default: packed straight from the edge list)")
     return p
 
 
@@ -71,6 +77,28 @@ def gin_forward(QGTC, bit_A, bit_X, W, n, D, bw):
     return QGTC.bitMM2Int(o, bit_W3, n, h2, out, bw, bw, False)
 
 
+def grouped_forward(QGTC, run_gin, A, X, tile_maps, W, ns, D, bw):
+    """The same six ops for ALL batches, op-major: op i of every batch is one grouped launch (QGTC.bitMM2*_grouped), so an
+    epoch is six kernels instead of six per batch.  Batches are independent and every op is the reference's op on the same
+    raw memory, so each batch's result is bit-identical to gcn_forward / gin_forward (main_qgtc.py:128-154)."""
+    bit_W1, bit_W2, bit_W3, h1, h2, out = W
+    B = len(A)
+    W1, W2, W3 = [bit_W1] * B, [bit_W2] * B, [bit_W3] * B
+    if run_gin:
+        o = QGTC.bitMM2Bit_grouped(A, X, ns, ns, D, 1, bw, bw, tile_maps)
+        o = QGTC.bitMM2Bit_grouped(o, W1, ns, [D] * B, h1, bw, bw, bw)
+        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps)
+        o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw)
+        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps)
+        return QGTC.bitMM2Int_grouped(o, W3, ns, [h2] * B, out, bw, bw, False)
+    o = QGTC.bitMM2Bit_grouped(X, W1, ns, [D] * B, h1, bw, bw, bw)
+    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps)
+    o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw)
+    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps)
+    o = QGTC.bitMM2Bit_grouped(o, W3, ns, [h2] * B, out, bw, bw, bw)
+    return QGTC.bitMM2Int_grouped(A, o, ns, ns, h2, 1, bw, False, tile_maps)
+
+
 def pack_weights(QGTC, feat_size, hidden, output, bw, device):
     """main_qgtc.py:100-110: all-ones weights, W3 in the output-layer (C8) format."""
     W_1 = torch.ones((feat_size, hidden), device=device)
@@ -84,7 +112,9 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def run(args, graph=None, quiet=False):
+def run(args, graph=None, quiet=False, ops=None):
+    """`ops` replaces the op module (default: this package's QGTC extension) -- e.g. the reference's own extension rebuilt for
+    sm_100a, for a same-box reference epoch (bench.py --impl reference)."""
     torch.manual_seed(3)
     np.random.seed(2)
     random.seed(2)
@@ -98,7 +128,8 @@ def run(args, graph=None, quiet=False):
     else:
         torch.cuda.set_device(args.gpu)
     device = torch.device("cuda", torch.cuda.current_device())
-    QGTC = qgtc_ppopp22_b200.load_extension()
+    QGTC = ops if ops is not None else qgtc_ppopp22_b200.load_extension()
+    ours = getattr(QGTC, "__backend__", None) == "qgtc_b200"
 
     if graph is None:
         if args.run_GIN and args.dataset in ("small-graphs", "Proteins-batched"):
@@ -111,7 +142,8 @@ def run(args, graph=None, quiet=False):
     counts = C.batch_node_counts(par_li, args.psize, args.batch_size)
     shards = C.shard_batches([float(n) * n for n in counts], world)      # dominant cost ~ n^2 * hidden
     it = C.ClusterIter(args.dataset, graph, args.psize, args.batch_size, None, use_pp=False, regular=args.regular,
-                       bit_width=args.bit_width, run_GIN=args.run_GIN, device=device, batch_ids=shards[rank], ops=QGTC, par_li=par_li)
+                       bit_width=args.bit_width, run_GIN=args.run_GIN, device=device, batch_ids=shards[rank], ops=QGTC, par_li=par_li,
+                       from_edges=ours and not getattr(args, "dense_pack", False), tile_bitmaps=ours)
 
     feat_size = graph.feat.shape[1]
     bw = args.bit_width
@@ -143,6 +175,19 @@ def run(args, graph=None, quiet=False):
             cur.wait_stream(st)
         return out
 
+    grouped = bool(getattr(args, "grouped", False)) and ours and len(it) > 0
+    if grouped:
+        gA = [c.bit_A for c in it.cTensor_li]
+        gX = [c.bit_X for c in it.cTensor_li]
+        gns = [p[0] for p in it.cluster_param_li]
+        mode = getattr(args, "tile_bitmap", "auto")
+        use_maps = it.tile_maps and (mode == "on" or (mode == "auto" and it.nonzero_tile_fraction() < 0.5))
+        gmaps = list(it.tile_maps) if use_maps else []
+
+        def one_epoch():  # noqa: F811  (op-major: six grouped launches)
+            res = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw)
+            return res[-1]
+
     if args.zerotile_jump:
         for cluster, param in it:
             QGTC.bitMM2Bit_base_cnt(cluster.bit_X, W[0], param[2], param[3], W[3], bw, bw, bw)
@@ -173,7 +218,8 @@ def run(args, graph=None, quiet=False):
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    result = {"epoch_ms": ms, "batches": len(it), "world": world,
+    result = {"epoch_ms": ms, "batches": len(it), "world": world, "grouped": grouped,
+              "tile_bitmaps_used": bool(grouped and gmaps), "nonzero_tile_fraction": it.nonzero_tile_fraction() if it.tile_maps else None,
               "checksum": float(last.sum().item()) if last is not None else 0.0, "nodes_per_batch": int(np.mean(counts))}
     if args.cpu_baseline and rank == 0:
         from qgtc_ppopp22_b200 import dgl_baseline

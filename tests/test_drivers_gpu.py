@@ -63,6 +63,40 @@ def test_epoch_runner_eager_and_graph():
     r3 = drv.run(a, graph=g, quiet=True)
     assert r1["batches"] == 3 and r1["epoch_ms"] > 0 and r2["epoch_ms"] > 0 and r3["epoch_ms"] > 0
     assert r1["checksum"] == r2["checksum"] == r3["checksum"]
+    # op-major (six grouped launches per epoch), eager and graph-captured, with and without the tile bitmaps
+    a.streams, a.cuda_graph, a.grouped = 1, False, True
+    r4 = drv.run(a, graph=g, quiet=True)
+    a.cuda_graph, a.tile_bitmap = True, "on"
+    r5 = drv.run(a, graph=g, quiet=True)
+    assert r4["grouped"] and r5["grouped"] and r5["tile_bitmaps_used"]
+    assert r4["checksum"] == r5["checksum"] == r1["checksum"]
+    a.run_GIN, a.cuda_graph, a.grouped = True, False, False
+    r6 = drv.run(a, graph=g, quiet=True)
+    a.cuda_graph, a.grouped = True, True
+    r7 = drv.run(a, graph=g, quiet=True)
+    assert r6["checksum"] == r7["checksum"]
+
+
+@pytest.mark.parametrize("run_gin", [False, True])
+def test_grouped_forward_equals_per_batch_forward(run_gin):
+    """main_qgtc.grouped_forward (one launch per op over all batches) == gcn_forward / gin_forward batch by batch."""
+    import qgtc_ppopp22_b200
+    from qgtc_ppopp22_b200 import cluster as C
+    from qgtc_ppopp22_b200 import main_qgtc as drv
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    g = C.make_synthetic_graph("tiny", 60)
+    par = C.shuffled_partitions(g, 60)
+    for bits in (1, 2, 4):
+        it = C.ClusterIter("tiny", g, 60, 20, None, bit_width=bits, run_GIN=run_gin, ops=QGTC, par_li=par, from_edges=True, tile_bitmaps=True)
+        D = g.feat.shape[1]
+        W = drv.pack_weights(QGTC, D, 16, 10, bits, torch.device("cuda"))
+        fwd = drv.gin_forward if run_gin else drv.gcn_forward
+        want = [fwd(QGTC, c.bit_A, c.bit_X, W, p[0], D, bits) for c, p in it]
+        A, X, ns = [c.bit_A for c in it.cTensor_li], [c.bit_X for c in it.cTensor_li], [p[0] for p in it.cluster_param_li]
+        for maps in ([], list(it.tile_maps)):
+            got = drv.grouped_forward(QGTC, run_gin, A, X, maps, W, ns, D, bits)
+            assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+        assert 0.0 < it.nonzero_tile_fraction() <= 1.0
 
 
 def test_cluster_iter_from_edges_matches_dense_path():
