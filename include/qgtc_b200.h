@@ -155,6 +155,19 @@ int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, 
                                 int count, int M, int K, int N, int bit1, int bit2, int out_bit,
                                 int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream);
 
+/* The same for several feature matrices per adjacency (e.g. one step of the bit-width sweep: 1/2/4/8-bit features of the
+ * same graphs): every group's adjacency is uploaded ONCE and multiplied with each variant's features.  Same results as
+ * `nvar` calls of qgtc_bitmm2bit_host_batched. */
+typedef struct qgtc_host_variant {
+    const int32_t* x2_host;
+    size_t x2_stride_words;
+    int bit2, out_bit;
+    int32_t* out_host;
+    size_t out_stride_words;
+} qgtc_host_variant;
+int qgtc_bitmm2bit_host_batched_multi(const int32_t* x1_host, size_t x1_stride_words, int count, int M, int K, int N, int bit1,
+                                      const qgtc_host_variant* variants, int nvar, int engine, unsigned flags, void* stream);
+
 /* Grouped bit-GEMM: ONE launch for `count` independent problems that share N, the bit widths and the kind of result but
  * have their own M, K, operands and output -- e.g. one op of the Cluster-GCN / batched-GIN forward for all batches of a
  * rank (the per-batch loop of main_qgtc.py:113-154 turned inside out: 6 launches per epoch instead of 6 x batches).

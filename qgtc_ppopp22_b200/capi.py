@@ -25,8 +25,14 @@ SYMBOLS = [
     "qgtc_val2bit", "qgtc_bit2val", "qgtc_bitmm2bit", "qgtc_bitmm2bit_col", "qgtc_bitmm2int",
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
-    "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit", "qgtc_bitmm_grouped",
+    "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit", "qgtc_bitmm_grouped", "qgtc_bitmm2bit_host_batched_multi",
 ]
+
+
+class HostVariant(ctypes.Structure):
+    """qgtc_host_variant (include/qgtc_b200.h)."""
+    _fields_ = [("x2_host", ctypes.c_void_p), ("x2_stride_words", ctypes.c_size_t), ("bit2", ctypes.c_int), ("out_bit", ctypes.c_int),
+                ("out_host", ctypes.c_void_p), ("out_stride_words", ctypes.c_size_t)]
 
 
 class GroupProblem(ctypes.Structure):
@@ -79,6 +85,7 @@ def lib() -> ctypes.CDLL:
         L.qgtc_tile_bitmap.argtypes = [vp, sz, sz, i, i, i, vp, sz, vp]
         L.qgtc_bitmm2bit_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2int_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
+        L.qgtc_bitmm2bit_host_batched_multi.argtypes = [vp, sz, i, i, i, i, i, c.POINTER(HostVariant), i, i, c.c_uint, vp]
         L.qgtc_bitmm_grouped.argtypes = [c.POINTER(GroupProblem), i, i, i, i, i, i, i, i, c.c_uint, vp]
         _LIB = L
     return _LIB
@@ -332,3 +339,24 @@ def bitmm_grouped(x1s, x2s, Ms, Ks, N, bit1, bit2, out_bit, kind=GROUP_BITS_ROW,
             p.M, p.K = int(Ms[k]), int(Ks[k])
         _check(lib().qgtc_bitmm_grouped(arr, count, N, bit1, bit2, out_bit, kind, int(bool(pad_128)), engine, flags, _stream()), "bitmm_grouped")
     return outs
+
+
+def bitMM2Bit_host_batched_multi(x1_host, x2_hosts, count, M, K, N, bit1, bit2s, out_bits, out_hosts=None, engine=ENGINE_AUTO, flags=0):
+    """One pipelined pass over `count` graphs for several feature matrices per graph (qgtc_bitmm2bit_host_batched_multi): the
+    adjacency is uploaded once per graph.  x1_host: [count, words]; x2_hosts[v]: [count, words_v]; returns the list of outputs."""
+    nvar = len(x2_hosts)
+    if nvar == 0 or nvar != len(bit2s) or nvar != len(out_bits):
+        raise QgtcError("variant lists must be non-empty and of equal length")
+    for t, n in [(x1_host, "bit_X1")] + [(x, "bit_X2[%d]" % v) for v, x in enumerate(x2_hosts)]:
+        if t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous() or t.dim() != 2 or t.shape[0] != count:
+            raise QgtcError("%s must be a contiguous [count, words] int32 CPU tensor" % n)
+    if out_hosts is None:
+        out_hosts = [torch.empty((count, packed_words(LAYOUT_ROW, ob, M, N)), dtype=torch.int32).pin_memory() for ob in out_bits]
+    arr = (HostVariant * nvar)()
+    for v in range(nvar):
+        arr[v].x2_host, arr[v].x2_stride_words = x2_hosts[v].data_ptr(), x2_hosts[v].shape[1]
+        arr[v].bit2, arr[v].out_bit = int(bit2s[v]), int(out_bits[v])
+        arr[v].out_host, arr[v].out_stride_words = out_hosts[v].data_ptr(), out_hosts[v].shape[1]
+    _check(lib().qgtc_bitmm2bit_host_batched_multi(x1_host.data_ptr(), x1_host.shape[1], count, M, K, N, bit1, arr, nvar, engine, flags, _stream()),
+           "bitMM2Bit_host_batched_multi")
+    return out_hosts

@@ -390,21 +390,29 @@ int qgtc_bitmm2bit_host(const int32_t* x1_host, size_t x1_words, const int32_t* 
     return QGTC_OK;
 }
 
-int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, const int32_t* x2_host, size_t x2_stride_words,
-                                int count, int M, int K, int N, int bit1, int bit2, int out_bit,
-                                int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream) {
-    if (!x1_host || !x2_host || !out_host || count <= 0) return QGTC_ERR_INVALID_ARG;
+int qgtc_bitmm2bit_host_batched_multi(const int32_t* x1_host, size_t x1_stride_words, int count, int M, int K, int N, int bit1,
+                                      const qgtc_host_variant* variants, int nvar, int engine, unsigned flags, void* stream) {
+    if (!x1_host || !variants || count <= 0 || nvar <= 0 || nvar > 16) return QGTC_ERR_INVALID_ARG;
     const size_t w1 = qgtc_packed_words(QGTC_LAYOUT_ROW, bit1, M, K);
-    const size_t w2 = qgtc_packed_words(QGTC_LAYOUT_COL128, bit2, K, N);
-    const size_t wo = qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, M, N);
-    if (!w1 || !w2 || !wo) return QGTC_ERR_INVALID_ARG;
-    if (x1_stride_words < w1 || x2_stride_words < w2 || out_stride_words < wo) return QGTC_ERR_SIZE;
+    if (!w1) return QGTC_ERR_INVALID_ARG;
+    if (x1_stride_words < w1) return QGTC_ERR_SIZE;
+    size_t w2[16], wo[16], per_problem = w1;
+    for (int v = 0; v < nvar; ++v) {
+        const qgtc_host_variant& q = variants[v];
+        if (!q.x2_host || !q.out_host) return QGTC_ERR_INVALID_ARG;
+        w2[v] = qgtc_packed_words(QGTC_LAYOUT_COL128, q.bit2, K, N);
+        wo[v] = qgtc_packed_words(QGTC_LAYOUT_ROW, q.out_bit, M, N);
+        if (!w2[v] || !wo[v]) return QGTC_ERR_INVALID_ARG;
+        if (q.x2_stride_words < w2[v] || q.out_stride_words < wo[v]) return QGTC_ERR_SIZE;
+        per_problem += w2[v] + wo[v];
+    }
     if (int rc = check_device()) return rc;
     cudaStream_t user = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_scratch_mu);
 
-    // two slots of `group` problems each: upload(g+1) | gemm(g) | download(g-1)
-    int group = (int)((48u << 20) / ((w1 + w2 + wo) * 4));
+    // two slots of `group` problems each: upload(g+1) | gemms(g) | download(g-1); the adjacency of a group is uploaded ONCE
+    // and used by every variant (bit width) of the step
+    int group = (int)((64u << 20) / (per_problem * 4));
     if (group < 1) group = 1;
     if (group > count) group = count;
     if (group > 64) group = 64;
@@ -412,7 +420,7 @@ int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, 
         const int v = std::atoi(ge);
         if (v >= 1 && v < group) group = v;
     }
-    const size_t slot_bytes = (((w1 + w2 + wo) * 4 * (size_t)group) + 255) & ~(size_t)255;
+    const size_t slot_bytes = ((per_problem * 4 * (size_t)group) + 255) & ~(size_t)255;
     void* base = nullptr;
     if (int rc = scratch_reserve(2 * slot_bytes, &base)) return rc;
 
@@ -444,20 +452,31 @@ int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, 
     for (int g = 0; g < ngroups && rc == QGTC_OK; ++g) {
         const int slot = g & 1, first = g * group, n = (count - first < group) ? count - first : group;
         char* d1 = reinterpret_cast<char*>(base) + (size_t)slot * slot_bytes;
-        char* d2 = d1 + w1 * 4 * (size_t)group;
-        char* d3 = d2 + w2 * 4 * (size_t)group;
         if (g >= 2) cudaStreamWaitEvent(s_up, ev_dn[slot], 0);      // the slot's previous results have left the device
         cudaError_t e = cudaMemcpy2DAsync(d1, w1 * 4, x1_host + (size_t)first * x1_stride_words, x1_stride_words * 4, w1 * 4, n, cudaMemcpyHostToDevice, s_up);
-        if (e == cudaSuccess) e = cudaMemcpy2DAsync(d2, w2 * 4, x2_host + (size_t)first * x2_stride_words, x2_stride_words * 4, w2 * 4, n, cudaMemcpyHostToDevice, s_up);
+        char* cur = d1 + w1 * 4 * (size_t)group;
+        char* d2[16];
+        char* d3[16];
+        for (int v = 0; v < nvar && e == cudaSuccess; ++v) {
+            const qgtc_host_variant& q = variants[v];
+            d2[v] = cur;
+            cur += w2[v] * 4 * (size_t)group;
+            d3[v] = cur;
+            cur += wo[v] * 4 * (size_t)group;
+            e = cudaMemcpy2DAsync(d2[v], w2[v] * 4, q.x2_host + (size_t)first * q.x2_stride_words, q.x2_stride_words * 4, w2[v] * 4, n, cudaMemcpyHostToDevice, s_up);
+        }
         if (e != cudaSuccess) { rc = record_cuda_error(e, "H2D(bitmm2bit_host_batched)"); break; }
         cudaEventRecord(ev_up[slot], s_up);
         cudaStreamWaitEvent(s_mm, ev_up[slot], 0);
-        rc = qgtc_bitmm2bit_batched(reinterpret_cast<int32_t*>(d1), w1, reinterpret_cast<int32_t*>(d2), w2, n, M, K, N, bit1, bit2, out_bit,
-                                    reinterpret_cast<int32_t*>(d3), wo, engine, flags, s_mm);
+        for (int v = 0; v < nvar && rc == QGTC_OK; ++v)
+            rc = qgtc_bitmm2bit_batched(reinterpret_cast<int32_t*>(d1), w1, reinterpret_cast<int32_t*>(d2[v]), w2[v], n, M, K, N, bit1, variants[v].bit2,
+                                        variants[v].out_bit, reinterpret_cast<int32_t*>(d3[v]), wo[v], engine, flags, s_mm);
         if (rc != QGTC_OK) break;
         cudaEventRecord(ev_mm[slot], s_mm);
         cudaStreamWaitEvent(s_dn, ev_mm[slot], 0);
-        e = cudaMemcpy2DAsync(out_host + (size_t)first * out_stride_words, out_stride_words * 4, d3, wo * 4, wo * 4, n, cudaMemcpyDeviceToHost, s_dn);
+        for (int v = 0; v < nvar && e == cudaSuccess; ++v)
+            e = cudaMemcpy2DAsync(variants[v].out_host + (size_t)first * variants[v].out_stride_words, variants[v].out_stride_words * 4, d3[v], wo[v] * 4,
+                                  wo[v] * 4, n, cudaMemcpyDeviceToHost, s_dn);
         if (e != cudaSuccess) { rc = record_cuda_error(e, "D2H(bitmm2bit_host_batched)"); break; }
         cudaEventRecord(ev_dn[slot], s_dn);
     }
@@ -466,6 +485,14 @@ int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(s_up);
     if (rc == QGTC_OK && e != cudaSuccess) rc = record_cuda_error(e, "sync(bitmm2bit_host_batched)");
     return rc;
+}
+
+int qgtc_bitmm2bit_host_batched(const int32_t* x1_host, size_t x1_stride_words, const int32_t* x2_host, size_t x2_stride_words,
+                                int count, int M, int K, int N, int bit1, int bit2, int out_bit,
+                                int32_t* out_host, size_t out_stride_words, int engine, unsigned flags, void* stream) {
+    if (!x1_host || !x2_host || !out_host || count <= 0) return QGTC_ERR_INVALID_ARG;
+    const qgtc_host_variant v{x2_host, x2_stride_words, bit2, out_bit, out_host, out_stride_words};
+    return qgtc_bitmm2bit_host_batched_multi(x1_host, x1_stride_words, count, M, K, N, bit1, &v, 1, engine, flags, stream);
 }
 
 int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,

@@ -51,6 +51,9 @@ constexpr int kMaxTasks = 2;                  // (chunk, column) conversion task
 constexpr int kMaxStagesG = 4;
 constexpr int kMaxCpsG = 4;
 constexpr int kGrpMaxProblems = 224;          // kernel-parameter table (64 B each): one launch takes up to this many problems
+constexpr int kUnitTable = 4096;              // launches of up to this many units carry a unit -> problem table (no search on the device)
+constexpr int kMaxUnitsPerCta = 384;          // per-CTA unit records in shared memory (64 B each); larger launches are split by the host
+constexpr int kTraceRoles = 8, kTraceEvents = 256;   // QGTC_GRP_TRACE=1: [role][event][tag, clock64] of CTA 0
 
 struct GrpProblem {
     const uint32_t* x1;
@@ -60,7 +63,7 @@ struct GrpProblem {
     unsigned long long x1_words, x2_words;    // words really present (zero-extension beyond)
     int M, K;
     int unit0;                                // index of this problem's first work unit
-    int pad_;
+    int mt;                                   // (per-CTA unit records only) the unit's 128-row tile
 };
 static_assert(sizeof(GrpProblem) == 64, "problem descriptors are 64 bytes");
 
@@ -69,11 +72,13 @@ struct GrpArgs {
     int N, NP, bit1, bit2, out_bit, epi, pad128;
     int cps, stages, dbufs, groups;           // chunks per item, A/B ring depth, accumulator buffers, expander groups in use
     int a_slot_bytes, b_slot_bytes, b_stage_bytes;
-    int off_bstage, off_bring, off_bars, off_flags, off_misc;   // shared-memory offsets from the 1024-byte aligned base
+    int off_bstage, off_bring, off_bars, off_flags, off_misc, off_units;   // shared-memory offsets from the 1024-byte aligned base
     unsigned int cps_inv;
     unsigned flags;
     unsigned int* error_flag;
+    unsigned long long* trace;                // clock64 trace buffer (debug instance only), else null
     GrpProblem p[kGrpMaxProblems];
+    unsigned short unit_z[kUnitTable];        // problem of unit u (valid when units <= kUnitTable)
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -91,83 +96,66 @@ __device__ __forceinline__ int piece_bytes(unsigned long long idx, unsigned long
     return left >= 4 ? 16 : (int)left * 4;
 }
 
-// The sequence of pipeline items of one CTA.  Every role walks it with its own Walk and must see the same sequence:
-// units u = blockIdx.x, blockIdx.x + gridDim.x, ...; inside a unit the stages (cps chunks each) in increasing order, all of
-// them without a tile bitmap, else stage 0 plus every stage with a non-zero chunk bit.
-struct Walk {
-    int tl, u, z, mt, gdk, nst;        // unit counter of this CTA, unit, problem, row tile, K chunks, stages of the problem
-    const uint32_t* bm;                // bitmap words of tile (z, mt), or null
-    int bmw, w, st_next, covered_end;  // stage iterator (see StageIter in gemm_tc05.cu)
-    uint32_t m;
-    bool first, in_unit, done;
-    int item;                          // number of items next() has returned so far (the last one's CTA-wide index + 1)
-
-    __device__ __forceinline__ void init() {
-        tl = -1; item = 0; nst = 0; st_next = 0; bm = nullptr; first = false; in_unit = false; done = false;
-        m = 0u; w = 0; bmw = 0; covered_end = 0; u = 0; z = 0; mt = 0; gdk = 0;
-    }
-
-    // position on this CTA's next unit; false when the work is exhausted
-    __device__ __forceinline__ bool next_unit(const GrpArgs& T) {
-        ++tl;
-        u = (int)blockIdx.x + tl * (int)gridDim.x;
-        if (u >= T.units) return false;
-        int lo = 0, hi = T.count - 1;      // largest z with unit0[z] <= u
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (T.p[mid].unit0 <= u) lo = mid; else hi = mid - 1;
-        }
-        z = lo;
-        mt = u - T.p[z].unit0;
-        gdk = s128(T.p[z].K);
-        nst = (gdk + T.cps - 1) / T.cps;
-        bmw = (gdk + 31) >> 5;
-        bm = T.p[z].bitmap ? T.p[z].bitmap + (size_t)mt * bmw : nullptr;
-        st_next = 0; w = -1; m = 0u; covered_end = 0; first = true;
-        return true;
-    }
-    // next stage of the current unit, or -1
-    __device__ __forceinline__ int next_stage(const GrpArgs& T) {
-        if (!bm) return st_next < nst ? st_next++ : -1;
-        if (first) { first = false; covered_end = T.cps; return 0; }
-        for (;;) {
-            if (m == 0u) {
-                if (++w >= bmw) return -1;
-                const int left = gdk - 32 * w;
-                const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-                m = __ldg(bm + w) & valid;
-                const int n = covered_end - 32 * w;
-                if (n > 0) m &= n >= 32 ? 0u : ~((1u << n) - 1u);
-                continue;
-            }
-            const int c = 32 * w + __ffs(m) - 1;
-            const int st = T.cps_inv ? (int)__umulhi((unsigned)c, T.cps_inv) : c;
-            covered_end = (st + 1) * T.cps;
-            const int n = covered_end - 32 * w;
-            m &= n >= 32 ? 0u : ~((1u << n) - 1u);
-            return st;
-        }
-    }
-    // next item of the CTA: (z, mt) are the fields above, c0 / nch its chunks.  false (for good) when the work is exhausted.
-    __device__ __forceinline__ bool next(const GrpArgs& T, int& c0, int& nch) {
-        for (;;) {
-            if (in_unit) {
-                const int st = next_stage(T);
-                if (st >= 0) {
-                    c0 = st * T.cps;
-                    nch = gdk - c0 < T.cps ? gdk - c0 : T.cps;
-                    ++item;
-                    return true;
-                }
-                in_unit = false;
-            }
-            if (done || !next_unit(T)) { done = true; return false; }
-            in_unit = true;
-        }
-    }
+// Per-CTA work lists, built in shared memory by the kernel prologue (all threads, before the dependency wait) so that the
+// role loops -- single warps running latency-bound instruction streams -- do no searching, dividing or bitmap walking:
+//   UnitRec  one per work unit of this CTA (units u = blockIdx.x, blockIdx.x + gridDim.x, ...): operand pointers, sizes, row tile
+//   ItemRec  one per pipeline item (a stage of cps K chunks of a unit), in processing order: all stages of a unit without a
+//            tile bitmap, else stage 0 (it initialises the accumulator) plus every stage with a non-zero chunk bit
+struct UnitRec {
+    const uint32_t* x1;
+    const uint32_t* x2;
+    void* out;
+    const uint32_t* bm;                       // bitmap words of this tile, or null
+    unsigned long long x1_words, x2_words;
+    int M, gdk, mt, item0;                    // rows, K chunks, 128-row tile, first item of the unit
 };
+static_assert(sizeof(UnitRec) == 64, "unit records are 64 bytes");
+struct ItemRec {
+    int c0;                                   // first K chunk
+    unsigned short unit;                      // index into the unit records
+    unsigned char nch, flags;                 // chunks (1..cps); bit 0: first item of its unit, bit 1: last
+};
+static_assert(sizeof(ItemRec) == 8, "item records are 8 bytes");
 
-template <bool A1>   // A1: single-plane A operand (the adjacency products): the lean expansion
+// stages of a tile with a bitmap: visit(stage) for stage 0 and every stage holding a non-zero chunk; returns their number
+template <typename F>
+__device__ __forceinline__ int walk_bitmap_stages(const uint32_t* bm, int gdk, int cps, unsigned cps_inv, F visit) {
+    int n = 1, covered_end = cps;
+    visit(0);
+    const int bmw = (gdk + 31) >> 5;
+    for (int w = 0; w < bmw; ++w) {
+        const int left = gdk - 32 * w;
+        uint32_t m = __ldg(bm + w) & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+        while (m) {
+            const int k = covered_end - 32 * w;          // chunks of this word already inside an emitted stage
+            if (k > 0) m &= k >= 32 ? 0u : ~((1u << k) - 1u);
+            if (!m) break;
+            const int c = 32 * w + __ffs(m) - 1;
+            const int st = cps_inv ? (int)__umulhi((unsigned)c, cps_inv) : c;
+            covered_end = (st + 1) * cps;
+            visit(st);
+            ++n;
+        }
+    }
+    return n;
+}
+
+#define QGTC_GTRACE(role, tag)                                                                              \
+    do {                                                                                                    \
+        if (TRACE && T.trace && blockIdx.x == 0 && tn < kTraceEvents) {                                     \
+            T.trace[((role) * kTraceEvents + tn) * 2] = (unsigned long long)(tag);                          \
+            T.trace[((role) * kTraceEvents + tn) * 2 + 1] = (unsigned long long)clock64();                  \
+            ++tn;                                                                                           \
+        }                                                                                                   \
+    } while (0)
+
+// fast path first: a plain try_wait (already-complete phases return at once), then the bounded suspending wait
+__device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity, unsigned int* ef, int where) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity, ef, where, true);
+}
+
+// A1: single-plane A operand (the adjacency products): the lean expansion.  TRACE: debug instance with a clock64 timeline of CTA 0.
+template <bool A1, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_constant__ GrpArgs T) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -184,6 +172,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     uint64_t* d_empty = d_full + 2;                // [2] 4 epilogue warps -> MMA
     volatile unsigned char* flags = smem + T.off_flags;   // [stage][chunk][lane quarter]: that 32 x 128-bit block has a one
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.off_misc);
+    int* n_items_slot = reinterpret_cast<int*>(smem + T.off_misc + 8);
+    UnitRec* units = reinterpret_cast<UnitRec*>(smem + T.off_units);          // [units of this CTA]
+    int tn = 0;                                    // trace cursor (per thread; lane 0 of the traced warps writes)
+    (void)tn;
+    const bool tlane = lane == 0;
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 1);
 
     // let the next kernel of the stream be scheduled as SMs free up (it waits for this grid in its own griddepcontrol.wait)
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
@@ -199,13 +193,79 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         fence_mbar_init();
     }
     if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 512);
+
+    // ---- work lists (kernel parameters only: nothing here depends on the previous kernel, so it runs before the wait below)
+    const int units_here = (T.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    ItemRec* items = reinterpret_cast<ItemRec*>(smem + T.off_units + units_here * (int)sizeof(UnitRec));
+    for (int k = threadIdx.x; k < units_here; k += kThreads) {
+        const int u = (int)blockIdx.x + k * (int)gridDim.x;
+        int z;
+        if (T.units <= kUnitTable) {
+            z = T.unit_z[u];
+        } else {
+            int lo = 0, hi = T.count - 1;      // largest z with unit0[z] <= u
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (T.p[mid].unit0 <= u) lo = mid; else hi = mid - 1;
+            }
+            z = lo;
+        }
+        const GrpProblem& P = T.p[z];
+        UnitRec r;
+        r.x1 = P.x1; r.x2 = P.x2; r.out = P.out;
+        r.x1_words = P.x1_words; r.x2_words = P.x2_words;
+        r.M = P.M;
+        r.gdk = s128(P.K);
+        r.mt = u - P.unit0;
+        r.bm = P.bitmap ? P.bitmap + (size_t)r.mt * ((r.gdk + 31) >> 5) : nullptr;
+        r.item0 = r.bm ? walk_bitmap_stages(r.bm, r.gdk, CPS, T.cps_inv, [](int) {}) : (r.gdk + CPS - 1) / CPS;   // count, for now
+        units[k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {        // exclusive scan of the per-unit item counts (one warp; a CTA has at most a few hundred units)
+        int carry = 0;
+        for (int base = 0; base < units_here; base += 32) {
+            const int k = base + lane;
+            const int c = k < units_here ? units[k].item0 : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (k < units_here) units[k].item0 = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) *n_items_slot = carry;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < units_here; k += kThreads) {
+        const UnitRec& r = units[k];
+        int i = r.item0;
+        const int gdk = r.gdk;
+        auto put = [&](int st) {
+            ItemRec it;
+            it.c0 = st * CPS;
+            it.unit = (unsigned short)k;
+            it.nch = (unsigned char)(gdk - it.c0 < CPS ? gdk - it.c0 : CPS);
+            it.flags = 0;
+            items[i++] = it;
+        };
+        if (r.bm) walk_bitmap_stages(r.bm, gdk, CPS, T.cps_inv, put);
+        else for (int st = 0; st * CPS < gdk; ++st) put(st);
+        items[r.item0].flags |= 1;
+        items[i - 1].flags |= 2;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int n_items = *n_items_slot;
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 2);
     // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (this kernel's
     // operands) are complete and visible only after this wait.  No-op for a normal launch.
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 3);
 
     const int dcols = T.dbufs * NP;                // accumulators first, then the A stages
     const int stage_cols = CPS * 32;
@@ -214,52 +274,52 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 
     if (warp < kExpWarps) {
         // ===================== A expanders =====================
+        // warp = (TMEM lane quarter q, group g); the groups take the items round-robin (G <= S: see gemm_tc05.cu).  A warp
+        // loads the rows it expands itself: cp.async into a lane-private ring, kARing - 1 of its own items ahead.
         const int q = warp & 3, g = warp >> 2;
         const int G = T.groups;
         if (g < G) {
-            unsigned char* ring = a_rings + (size_t)warp * kARing * T.a_slot_bytes;
-            Walk ld, cs;
-            ld.init();
-            cs.init();
-            // issue the cp.async loads of an item into a ring slot: piece (p, j) of this lane's row at [(p * CPS + j) * 32 + lane] x 16 B
-            auto issue = [&](const Walk& wk, int c0, int nch, int slot) {
-                const GrpProblem& P = T.p[wk.z];
-                const int m = wk.mt * 128 + 32 * q + lane;
-                const unsigned long long gdk4 = (unsigned long long)wk.gdk * 4;
-                const unsigned long long act_offset = (unsigned long long)p8(P.M) * gdk4;     // reference kernel.h:265
-                const bool row_ok = m < p8(P.M);
-                unsigned char* dst = ring + (size_t)slot * T.a_slot_bytes + lane * 16;
-                for (int p = 0; p < T.bit1; ++p) {
-                    for (int j = 0; j < nch; ++j) {
-                        const unsigned long long idx = (unsigned long long)p * act_offset + (unsigned long long)m * gdk4 + 4ull * (c0 + j);
-                        const int nb = row_ok ? piece_bytes(idx, P.x1_words) : 0;
-                        cp_async16_zfill(dst + (size_t)(p * CPS + j) * 512, nb ? (const void*)(P.x1 + idx) : (const void*)P.x1, nb);
+            unsigned char* ring = a_rings + (size_t)warp * kARing * T.a_slot_bytes + lane * 16;   // piece i of this lane at + i * 512
+            const int trole = warp == 0 ? 0 : (warp == 4 ? 1 : -1);
+            const bool tr = TRACE && trole >= 0 && tlane;
+            if (tr) QGTC_GTRACE(trole, 10);
+            int s = g % S;                         // stage and use count of the item being consumed
+            uint32_t use = (uint32_t)(g / S);
+            // software pipeline: iteration k issues the loads of own item k and consumes own item k - (kARing - 1)
+            int it_l = g, slot_l = 0, slot_c = 0;
+#pragma unroll 1
+            for (int it_c = g - (kARing - 1) * G; it_c < n_items; it_c += G, it_l += G) {
+                if (it_l < n_items) {
+                    const ItemRec I = items[it_l];
+                    const UnitRec& U = units[I.unit];
+                    const int m = U.mt * 128 + 32 * q + lane;
+                    const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
+                    const unsigned long long act_offset = (unsigned long long)p8(U.M) * gdk4;          // reference kernel.h:265
+                    const unsigned long long idx0 = (unsigned long long)m * gdk4 + 4ull * I.c0;
+                    const bool row_ok = m < p8(U.M);
+                    unsigned char* dst = ring + slot_l * T.a_slot_bytes;
+                    const int nb1 = A1 ? 1 : T.bit1;
+                    if (row_ok && idx0 + (unsigned long long)(nb1 - 1) * act_offset + 4ull * I.nch <= U.x1_words) {   // all pieces inside the tensor
+                        for (int p = 0; p < nb1; ++p)
+                            for (int j = 0; j < I.nch; ++j)
+                                cp_async16_zfill(dst + (p * CPS + j) * 512, U.x1 + idx0 + (unsigned long long)p * act_offset + 4 * j, 16);
+                    } else {
+                        for (int p = 0; p < nb1; ++p)
+                            for (int j = 0; j < I.nch; ++j) {
+                                const unsigned long long idx = idx0 + (unsigned long long)p * act_offset + 4ull * j;
+                                const int nb = row_ok ? piece_bytes(idx, U.x1_words) : 0;
+                                cp_async16_zfill(dst + (p * CPS + j) * 512, nb ? (const void*)(U.x1 + idx) : (const void*)U.x1, nb);
+                            }
                     }
+                    if (++slot_l == kARing) slot_l = 0;
                 }
-            };
-            // advance a walk to this group's next item (items are dealt to the groups round-robin)
-            auto next_own = [&](Walk& wk, int& c0, int& nch) -> bool {
-                while (wk.next(T, c0, nch))
-                    if ((wk.item - 1) % G == g) return true;
-                return false;
-            };
-            int lc0 = 0, lnch = 0;
-            bool more = true;
-#pragma unroll 1
-            for (int i = 0; i < kARing - 1; ++i) {
-                if (more && (more = next_own(ld, lc0, lnch))) issue(ld, lc0, lnch, i);
                 cp_async_commit();
-            }
-            int k = 0, c0 = 0, nch = 0;
-#pragma unroll 1
-            while (next_own(cs, c0, nch)) {
-                if (more && (more = next_own(ld, lc0, lnch))) issue(ld, lc0, lnch, (k + kARing - 1) % kARing);
-                cp_async_commit();
-                cp_async_wait<kARing - 1>();       // this lane's pieces of item k have landed (only this lane reads them)
-                const int it = cs.item - 1;        // CTA-wide item index: stage and phase
-                const int s = it % S;
-                const uint32_t use = (uint32_t)(it / S);
-                const unsigned char* src = ring + (size_t)(k % kARing) * T.a_slot_bytes + lane * 16;
+                if (it_c < 0) continue;
+                cp_async_wait<kARing - 1>();       // this lane's pieces of item it_c have landed (only this lane reads them)
+                if (tr) QGTC_GTRACE(trole, 12);
+                const int nch = items[it_c].nch;
+                const unsigned char* src = ring + slot_c * T.a_slot_bytes;
+                if (++slot_c == kARing) slot_c = 0;
                 const uint32_t st_s = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + s * stage_cols);
                 unsigned nzmask = 0;
 #pragma unroll 1
@@ -267,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     uint32_t r[32];
                     uint32_t any;
                     if (A1) {
-                        const uint4 pv = *reinterpret_cast<const uint4*>(src + (size_t)j * 512);
+                        const uint4 pv = *reinterpret_cast<const uint4*>(src + j * 512);
                         const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
                         any = pv.x | pv.y | pv.z | pv.w;
 #pragma unroll
@@ -280,8 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                         any = 0u;
 #pragma unroll
                         for (int e = 0; e < 32; ++e) r[e] = 0u;
+#pragma unroll 1
                         for (int p = 0; p < T.bit1; ++p) {
-                            const uint4 pv = *reinterpret_cast<const uint4*>(src + (size_t)(p * CPS + j) * 512);
+                            const uint4 pv = *reinterpret_cast<const uint4*>(src + (p * CPS + j) * 512);
                             const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
                             any |= pv.x | pv.y | pv.z | pv.w;
 #pragma unroll
@@ -293,8 +354,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     }
                     if (nojump || __any_sync(0xffffffffu, any != 0u)) nzmask |= 1u << j;
                     if (j == 0) {   // the first chunk is expanded before the wait: only the store sits behind it
-                        mbar_wait<32>(&empty[s], (use & 1) ^ 1, ef, 1, true);     // the MMAs of this stage's previous use are done
+                        if (tr) QGTC_GTRACE(trole, 13);
+                        gwait(&empty[s], (use & 1) ^ 1, ef, 1);     // the MMAs of this stage's previous use are done
                         tc_fence_after();
+                        if (tr) QGTC_GTRACE(trole, 14);
                     }
                     tmem_st32(st_s + (uint32_t)(32 * j), r);
                 }
@@ -303,63 +366,72 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
-                ++k;
+                if (tr) QGTC_GTRACE(trole, 15);
+                s += G;
+                if (s >= S) { s -= S; ++use; }
             }
             cp_async_wait<0>();
         }
     } else if (warp >= kConvWarp0 && warp < kConvWarp0 + kConvWarps) {
         // ===================== B converters =====================
-        // thread t takes the (chunk, column) tasks t, t + 128 of every item: bit2 pieces of 16 B (128 K bits of one column,
+        // thread t takes the (chunk, column) tasks t and t + 128 of every item: bit2 pieces of 16 B (128 K bits of one column,
         // one plane each) in, 128 u8 values in the MMA's K order out, as 8 core-matrix rows of 16 B.
         const int t = threadIdx.x - kConvWarp0 * 32;
-        Walk ld, cs;
-        ld.init();
-        cs.init();
         const int p8n = p8(T.N);
-        auto issue = [&](const Walk& wk, int c0, int nch, int slot) {
-            const GrpProblem& P = T.p[wk.z];
-            const unsigned long long gdk4 = (unsigned long long)wk.gdk * 4;
-            const unsigned long long w_offset = gdk4 * (unsigned long long)(T.pad128 ? p128(T.N) : p8n);   // kernel.h:266 / :836
-            unsigned char* dst = b_ring + (size_t)slot * T.b_slot_bytes + t * 16;
-            for (int i = 0; i < kMaxTasks; ++i) {
-                const int task = t + i * kConvThreads;
-                if (task >= nch * NP) break;
-                const int j = task / NP, n = task - j * NP;
-                for (int qq = 0; qq < T.bit2; ++qq) {
-                    const unsigned long long idx = (unsigned long long)qq * w_offset + (unsigned long long)n * gdk4 + 4ull * (c0 + j);
-                    const int nb = n < p8n ? piece_bytes(idx, P.x2_words) : 0;
-                    cp_async16_zfill(dst + (size_t)(i * T.bit2 + qq) * (kConvThreads * 16), nb ? (const void*)(P.x2 + idx) : (const void*)P.x2, nb);
-                }
-            }
-        };
-        int lc0 = 0, lnch = 0;
-        bool more = true;
-#pragma unroll 1
-        for (int i = 0; i < kBRing - 1; ++i) {
-            if (more && (more = ld.next(T, lc0, lnch))) issue(ld, lc0, lnch, i);
-            cp_async_commit();
+        const int pn = T.pad128 ? p128(T.N) : p8n;                     // columns per plane of X2: kernel.h:266 / :836
+        int tj[kMaxTasks], tn_[kMaxTasks];                             // this thread's tasks: chunk within the item, column
+#pragma unroll
+        for (int i = 0; i < kMaxTasks; ++i) {
+            const int task = t + i * kConvThreads;
+            tj[i] = task / NP;
+            tn_[i] = task - tj[i] * NP;
         }
-        int k = 0, c0 = 0, nch = 0;
+        unsigned char* ring = b_ring + t * 16;                         // piece (i, plane) of this thread at + (i * bit2 + plane) * 2048
+        const bool tr = TRACE && warp == kConvWarp0 && tlane;
+        if (tr) QGTC_GTRACE(2, 20);
+        int s = 0, slot_l = 0, slot_c = 0;
+        uint32_t use = 0;
 #pragma unroll 1
-        while (cs.next(T, c0, nch)) {
-            if (more && (more = ld.next(T, lc0, lnch))) issue(ld, lc0, lnch, (k + kBRing - 1) % kBRing);
+        for (int it_c = -(kBRing - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
+            if (it_l < n_items) {
+                const ItemRec I = items[it_l];
+                const UnitRec& U = units[I.unit];
+                const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
+                const unsigned long long w_offset = gdk4 * (unsigned long long)pn;
+                unsigned char* dst = ring + slot_l * T.b_slot_bytes;
+#pragma unroll
+                for (int i = 0; i < kMaxTasks; ++i) {
+                    if (tj[i] < I.nch) {
+                        const unsigned long long idx0 = (unsigned long long)tn_[i] * gdk4 + 4ull * (I.c0 + tj[i]);
+                        const bool col_ok = tn_[i] < p8n;
+                        for (int qq = 0; qq < T.bit2; ++qq) {
+                            const unsigned long long idx = idx0 + (unsigned long long)qq * w_offset;
+                            const int nb = col_ok ? piece_bytes(idx, U.x2_words) : 0;
+                            cp_async16_zfill(dst + (i * T.bit2 + qq) * (kConvThreads * 16), nb ? (const void*)(U.x2 + idx) : (const void*)U.x2, nb);
+                        }
+                    }
+                }
+                if (++slot_l == kBRing) slot_l = 0;
+            }
             cp_async_commit();
+            if (it_c < 0) continue;
             cp_async_wait<kBRing - 1>();
-            const int s = k % S;
-            const uint32_t use = (uint32_t)(k / S);
-            mbar_wait<32>(&empty[s], (use & 1) ^ 1, ef, 2, true);        // the MMAs that read this stage's previous content are done
-            const unsigned char* src = b_ring + (size_t)(k % kBRing) * T.b_slot_bytes + t * 16;
+            if (tr) QGTC_GTRACE(2, 22);
+            const int nch = items[it_c].nch;
+            gwait(&empty[s], (use & 1) ^ 1, ef, 2);                    // the MMAs that read this stage's previous content are done
+            if (tr) QGTC_GTRACE(2, 23);
+            const unsigned char* src = ring + slot_c * T.b_slot_bytes;
+            if (++slot_c == kBRing) slot_c = 0;
             unsigned char* stage = b_stages + (size_t)s * T.b_stage_bytes;
-#pragma unroll 1
+#pragma unroll
             for (int i = 0; i < kMaxTasks; ++i) {
-                const int task = t + i * kConvThreads;
-                if (task >= nch * NP) break;
-                const int j = task / NP, n = task - j * NP;
+                if (tj[i] >= nch) continue;
                 uint32_t o[32];
 #pragma unroll
                 for (int e = 0; e < 32; ++e) o[e] = 0u;
+#pragma unroll 1
                 for (int qq = 0; qq < T.bit2; ++qq) {
-                    const uint4 pv = *reinterpret_cast<const uint4*>(src + (size_t)(i * T.bit2 + qq) * (kConvThreads * 16));
+                    const uint4 pv = *reinterpret_cast<const uint4*>(src + (i * T.bit2 + qq) * (kConvThreads * 16));
                     const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
                     // byte i of o[8 s + c] = value of K element 32 s + c + 8 i (the expanders' K permutation)
 #pragma unroll
@@ -369,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     }
                 }
                 // image of one K chunk: [k group (8)][column block][8 columns][16 B]; k group kg = registers 4 kg .. 4 kg + 3
-                unsigned char* dstc = stage + (size_t)j * NP * 128 + (size_t)(n >> 3) * 128 + (n & 7) * 16;
+                unsigned char* dstc = stage + (size_t)tj[i] * NP * 128 + (size_t)(tn_[i] >> 3) * 128 + (tn_[i] & 7) * 16;
 #pragma unroll
                 for (int kg = 0; kg < 8; ++kg)
                     *reinterpret_cast<uint4*>(dstc + (size_t)kg * (NP / 8) * 128) = make_uint4(o[4 * kg], o[4 * kg + 1], o[4 * kg + 2], o[4 * kg + 3]);
@@ -377,7 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
-            ++k;
+            if (tr) QGTC_GTRACE(2, 24);
+            if (++s == S) { s = 0; ++use; }
         }
         cp_async_wait<0>();
     } else if (warp == kIssuerWarp) {
@@ -387,67 +460,67 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const uint64_t desc0 = make_smem_desc(smem_u32(b_stages), lbo, sbo);
         const uint32_t desc_hi = (uint32_t)(desc0 >> 32), lo0 = (uint32_t)desc0;
         const uint32_t stage_lo = (uint32_t)T.b_stage_bytes >> 4, chunk_lo = ((uint32_t)NP * 128u) >> 4, kstep_lo = (2u * lbo) >> 4;
-        Walk wk;
-        wk.init();
         int s = 0, buf = 0;
-        uint32_t use = 0, duse = 0;
+        uint32_t use = 0, duse = 0, started = 0;
 #pragma unroll 1
-        while (wk.next_unit(T)) {
-            mbar_wait(&d_empty[buf], (duse & 1) ^ 1, ef, 3, true);       // the epilogue has drained this accumulator's previous tile
-            tc_fence_after();
+        for (int it = 0; it < n_items; ++it) {
+            const ItemRec I = items[it];
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NP);
-            uint32_t started = 0;                                         // 0: the next MMA overwrites the accumulator
-#pragma unroll 1
-            for (int st; (st = wk.next_stage(T)) >= 0;) {
-                const int c_first = st * CPS;
-                const int nch = wk.gdk - c_first < CPS ? wk.gdk - c_first : CPS;
-                mbar_wait(&full[s], use & 1, ef, 4, true);
-                tc_fence_after();
-                const uint32_t fw = lane < kMaxCpsG ? *reinterpret_cast<volatile uint32_t*>(smem + T.off_flags + (s * kMaxCpsG + lane) * 4) : 0u;
-                const uint32_t m4 = __ballot_sync(0xffffffffu, fw != 0u);
+            if (I.flags & 1) {
+                if (tlane) QGTC_GTRACE(3, 30);
+                gwait(&d_empty[buf], (duse & 1) ^ 1, ef, 3);             // the epilogue has drained this accumulator's previous tile
+                started = 0;                                             // the unit's first MMA overwrites the accumulator
+            }
+            gwait(&full[s], use & 1, ef, 4);
+            tc_fence_after();
+            if (tlane) QGTC_GTRACE(3, 32);
+            const int nch = I.nch;
+            const uint32_t fw = lane < kMaxCpsG ? *reinterpret_cast<volatile uint32_t*>(smem + T.off_flags + (s * kMaxCpsG + lane) * 4) : 0u;
+            // an all-zero chunk adds nothing and is skipped -- except the unit's very first MMAs, which initialise D
+            uint32_t todo = __ballot_sync(0xffffffffu, fw != 0u) & ((1u << nch) - 1u);
+            if (!started) todo |= 1u;
+            if (elect_one()) {
                 const uint32_t a_tmem = tmem_base + (uint32_t)(dcols + s * stage_cols);
                 const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
-                // an all-zero chunk adds nothing and is skipped -- except the unit's very first MMAs, which initialise D
-                uint32_t todo = m4 & ((1u << nch) - 1u);
-                if (!started) todo |= 1u;
-                if (elect_one()) {
-                    uint32_t acc = started;
+                uint32_t acc = started;
 #pragma unroll 1
-                    for (int j = 0; j < nch; ++j) {
-                        if ((todo >> j) & 1u) {
+                for (int j = 0; j < nch; ++j) {
+                    if ((todo >> j) & 1u) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
-                                mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, acc);
-                                acc = 1u;
-                            }
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                            mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, acc);
+                            acc = 1u;
                         }
                     }
-                    tc_commit(&empty[s]);          // arrives when these MMAs have finished reading A (TMEM) and B (smem)
                 }
-                started = 1u;                      // todo != 0 whenever started was 0
-                __syncwarp();
-                if (++s == S) { s = 0; ++use; }
+                tc_commit(&empty[s]);          // arrives when these MMAs have finished reading A (TMEM) and B (smem)
+                if (I.flags & 2) tc_commit(&d_full[buf]);
             }
-            if (elect_one()) tc_commit(&d_full[buf]);
+            started = 1u;                      // todo != 0 whenever started was 0
             __syncwarp();
-            if (++buf == T.dbufs) { buf = 0; ++duse; }
+            if (tlane) QGTC_GTRACE(3, 33);
+            if (++s == S) { s = 0; ++use; }
+            if (I.flags & 2) {
+                if (++buf == T.dbufs) { buf = 0; ++duse; }
+            }
         }
     } else {
         // ===================== epilogue (4 warps: one per TMEM lane quarter) =====================
         const int q = warp & 3;
         const int N = T.N, ob = T.out_bit;
-        Walk wk;
-        wk.init();
         int buf = 0;
         uint32_t duse = 0;
 #pragma unroll 1
-        while (wk.next_unit(T)) {
-            const GrpProblem& P = T.p[wk.z];
+        for (int tl = 0; tl < units_here; ++tl) {
+            const UnitRec& P = units[tl];
             const int M = P.M;
-            const int m = wk.mt * 128 + 32 * q + lane;
-            mbar_wait<256>(&d_full[buf], duse & 1, ef, 6, false);
+            const int m = P.mt * 128 + 32 * q + lane;
+            const bool tr = TRACE && warp == kEpiWarp0 && tlane;
+            if (tr) QGTC_GTRACE(4, 40);
+            mbar_wait<64>(&d_full[buf], duse & 1, ef, 6, false);
             tc_fence_after();
+            if (tr) QGTC_GTRACE(4, 41);
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
             if (T.epi == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out);
@@ -490,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 uint32_t* out = reinterpret_cast<uint32_t*>(P.out);
                 const unsigned long long kw = (unsigned long long)s128(M) * 4;
                 const unsigned long long plane = kw * (unsigned long long)p128(N);
-                const int mw = wk.mt * 4 + q;
+                const int mw = P.mt * 4 + q;
                 const unsigned keep = (1u << ob) - 1u;
                 if ((unsigned long long)mw < kw) {
                     for (int cb = 0; cb < NP / 16; ++cb) {
@@ -513,12 +586,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);
+            if (tr) QGTC_GTRACE(4, 42);
             if (++buf == T.dbufs) { buf = 0; ++duse; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 4);
     if (warp == kIssuerWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -526,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 }
 
 struct GrpPlan {
-    int NP, cps, stages, dbufs, groups, a_slot, b_slot, b_stage, off_bstage, off_bring, off_bars, off_flags, off_misc, smem_total;
+    int NP, cps, stages, dbufs, groups, a_slot, b_slot, b_stage, off_bstage, off_bring, off_bars, off_flags, off_misc, off_units, smem_total;
 };
 
 // pipeline geometry for (N, bit1, bit2); false when the shape does not fit this engine
@@ -558,8 +633,9 @@ bool plan_for(int N, int bit1, int bit2, GrpPlan& pl) {
         off += kMaxStagesG * kMaxCpsG * 4;
         pl.off_misc = off;
         off += 16;
+        pl.off_units = off;                      // per-CTA work lists (unit + item records): sized at launch
         pl.smem_total = off + 1024;              // slack for the manual 1024-byte alignment
-        if (pl.smem_total <= 224 * 1024) return true;
+        if (pl.smem_total + 4 * 1024 <= 227 * 1024) return true;
     }
     return false;
 }
@@ -581,28 +657,54 @@ bool grp_supports(int N, int bit1, int bit2, int epi) {
     return plan_for(N, bit1, bit2, pl);
 }
 
+unsigned long long* g_grp_trace = nullptr;     // clock64 trace buffer of the debug instance (QGTC_GRP_TRACE=1)
+constexpr size_t kGrpTraceWords = (size_t)kTraceRoles * kTraceEvents * 2;
+
 // One op over `count` problems.  Returns QGTC_ERR_UNSUPPORTED (before any work is enqueued) when the shape does not fit.
 int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int bit1, int bit2, int out_bit, int epi, int pad128,
                         unsigned flags, cudaStream_t st) {
     GrpPlan pl;
     if (count <= 0) return QGTC_ERR_INVALID_ARG;
     if (!grp_supports(N, bit1, bit2, epi) || !plan_for(N, bit1, bit2, pl)) return QGTC_ERR_UNSUPPORTED;
+    for (int i = 0; i < count; ++i)    // a single problem larger than one launch can hold: not this engine
+        if ((long long)((p8(probs[i].M) + 127) / 128) > (long long)kNumSMs * kMaxUnitsPerCta) return QGTC_ERR_UNSUPPORTED;
     unsigned int* ef = tc05_error_flag_device();
-    static thread_local GrpArgs T;     // 14 KB: filled per launch, passed by value as the kernel parameter
-    for (int first = 0; first < count; first += kGrpMaxProblems) {
-        const int n = count - first < kGrpMaxProblems ? count - first : kGrpMaxProblems;
+    static const bool want_trace = [] { const char* t = getenv("QGTC_GRP_TRACE"); return t && t[0] == '1'; }();
+    if (want_trace && !g_grp_trace && cudaMalloc(&g_grp_trace, kGrpTraceWords * 8) != cudaSuccess) { cudaGetLastError(); g_grp_trace = nullptr; }
+    static thread_local GrpArgs T;     // ~23 KB: filled per launch, passed by value as the kernel parameter
+    int first = 0;
+    int limit = kGrpMaxProblems;       // problems per launch; halved when the per-CTA work lists would not fit shared memory
+    while (first < count) {
+        // as many problems as the parameter table and the per-CTA work lists hold
         long long units = 0;
-        for (int i = 0; i < n; ++i) {
-            const GroupedProblemHost& h = probs[first + i];
-            GrpProblem& p = T.p[i];
+        int n = 0, max_nst = 1;
+        while (first + n < count && n < limit) {
+            const GroupedProblemHost& h = probs[first + n];
+            const long long u = (p8(h.M) + 127) / 128;
+            if (n > 0 && units + u > (long long)kNumSMs * kMaxUnitsPerCta) break;
+            GrpProblem& p = T.p[n];
             p.x1 = h.x1; p.x2 = h.x2; p.out = h.out;
             p.bitmap = bit1 == 1 ? h.bitmap : nullptr;
             p.x1_words = h.x1_words; p.x2_words = h.x2_words;
             p.M = h.M; p.K = h.K;
             p.unit0 = (int)units;
-            p.pad_ = 0;
-            units += (p8(h.M) + 127) / 128;
-            if (units > (1ll << 30)) return QGTC_ERR_UNSUPPORTED;
+            p.mt = 0;
+            if (units + u <= kUnitTable)
+                for (long long k = 0; k < u; ++k) T.unit_z[units + k] = (unsigned short)n;
+            const int nst = (s128(h.K) + pl.cps - 1) / pl.cps;
+            if (nst > max_nst) max_nst = nst;
+            units += u;
+            ++n;
+        }
+        {
+            const long long grid_ = units < kNumSMs ? units : kNumSMs;
+            const long long upc = (units + grid_ - 1) / grid_;
+            const long long lists = upc * (long long)sizeof(UnitRec) + upc * max_nst * (long long)sizeof(ItemRec);
+            if (pl.smem_total + lists > 227 * 1024) {
+                if (n <= 1) return QGTC_ERR_UNSUPPORTED;
+                limit = n / 2;
+                continue;              // retry this launch with fewer problems
+            }
         }
         T.count = n;
         T.units = (int)units;
@@ -610,16 +712,22 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         T.cps = pl.cps; T.stages = pl.stages; T.dbufs = pl.dbufs; T.groups = pl.groups;
         T.a_slot_bytes = pl.a_slot; T.b_slot_bytes = pl.b_slot; T.b_stage_bytes = pl.b_stage;
         T.off_bstage = pl.off_bstage; T.off_bring = pl.off_bring; T.off_bars = pl.off_bars; T.off_flags = pl.off_flags; T.off_misc = pl.off_misc;
+        T.off_units = pl.off_units;
         T.cps_inv = pl.cps == 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)pl.cps - 1ull) / (unsigned long long)pl.cps);
         T.flags = flags;
         T.error_flag = ef;
+        T.trace = g_grp_trace;
+        if (g_grp_trace) cudaMemsetAsync(g_grp_trace, 0, kGrpTraceWords * 8, st);
+        const int grid = T.units < kNumSMs ? T.units : kNumSMs;
+        const int units_per_cta = (T.units + grid - 1) / grid;
+        const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * (int)sizeof(ItemRec);
         auto launch = [&](auto kfn) -> int {
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_total);
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return record_cuda_error(e, "cudaFuncSetAttribute(gemm_grp)");
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(T.units < kNumSMs ? T.units : kNumSMs);
+            cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(kThreads);
-            cfg.dynamicSmemBytes = pl.smem_total;
+            cfg.dynamicSmemBytes = smem_total;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
@@ -632,10 +740,22 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             if (e != cudaSuccess) return record_cuda_error(e, "cudaLaunchKernelEx(gemm_grp)");
             return check_launch("gemm_grp_kernel");
         };
-        const int rc = bit1 == 1 ? launch(gemm_grp_kernel<true>) : launch(gemm_grp_kernel<false>);
+        int rc;
+        if (g_grp_trace) rc = bit1 == 1 ? launch(gemm_grp_kernel<true, true>) : launch(gemm_grp_kernel<false, true>);
+        else rc = bit1 == 1 ? launch(gemm_grp_kernel<true, false>) : launch(gemm_grp_kernel<false, false>);
         if (rc != QGTC_OK) return rc;
+        first += n;
     }
     return QGTC_OK;
+}
+
+// debugging aid (not part of the public ABI): copy the last clock64 trace of the grouped engine to the host
+extern "C" int qgtc_debug_grp_trace(unsigned long long* dst, size_t max_words) {
+    if (!g_grp_trace) return 0;
+    const size_t n = max_words < kGrpTraceWords ? max_words : kGrpTraceWords;
+    cudaDeviceSynchronize();
+    cudaMemcpy(dst, g_grp_trace, n * 8, cudaMemcpyDeviceToHost);
+    return (int)n;
 }
 
 }  // namespace qgtc

@@ -49,6 +49,7 @@ def build_parser():
                    help="issue the epoch op-major: ONE grouped launch per op over all of this rank's batches (6 launches per epoch)")
     p.add_argument("--tile-bitmap", choices=["auto", "on", "off"], default="auto",
                    help="--grouped: pass the batches' tile bitmaps (zero-tile jumping); auto = when under half of the tiles are non-zero")
+    p.add_argument("--min-region-ms", type=float, default=0.0, help="--cuda-graph: replay enough epochs for a timed region of at least this many ms")
     p.add_argument("--dense-pack", action="store_true", help="build batches through the dense fp32 n x n adjacency as sampler.py:87-89 does "
                                                               "(default: packed straight from the edge list)")
     return p
@@ -194,6 +195,8 @@ def run(args, graph=None, quiet=False, ops=None):
             QGTC.bitMM2Bit_zerojump_cnt(cluster.bit_X, W[0], param[2], param[3], W[3], bw, bw, bw)
         return {"epoch_ms": None}
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_timed = args.n_epochs
     if args.cuda_graph:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -204,21 +207,52 @@ def run(args, graph=None, quiet=False, ops=None):
         graph_obj = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph_obj):
             last = one_epoch()
+        for _ in range(3):
+            graph_obj.replay()
+        torch.cuda.synchronize()
+        min_region_ms = float(getattr(args, "min_region_ms", 0.0) or 0.0)
+        if min_region_ms > 0:                                             # size the timed region: replays are tens of microseconds
+            e0.record()
+            for _ in range(20):
+                graph_obj.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            est = max(e0.elapsed_time(e1) / 20, 1e-3)
+            n_timed = max(n_timed, int(min_region_ms / est) + 1)
+            if world > 1:                                                 # every rank replays the same number of epochs
+                import torch.distributed as dist
+                t = torch.tensor([n_timed], dtype=torch.int64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                n_timed = int(t.item())
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
         torch.cuda.synchronize()
         start_time = time.time()
-        for _ in range(args.n_epochs):
+        e0.record()
+        for _ in range(n_timed):
             graph_obj.replay()
+        e1.record()
     else:
-        for _ in range(args.n_epochs):
+        e0.record()
+        for _ in range(n_timed):
             last = one_epoch()
+        e1.record()
     torch.cuda.synchronize()
-    ms = (time.time() - start_time) * 1000 / args.n_epochs
+    ms = (time.time() - start_time) * 1000 / n_timed                      # the reference's convention (main_qgtc.py:157-159)
+    ms_dev = e0.elapsed_time(e1) / n_timed                                # device time of the same epochs (CUDA events on the launching stream)
+    rank_ms = [ms_dev]
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    result = {"epoch_ms": ms, "batches": len(it), "world": world, "grouped": grouped,
+        allr = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(allr, torch.tensor([ms_dev], dtype=torch.float64, device=device))
+        rank_ms = [float(x.item()) for x in allr]
+        ms_dev = max(rank_ms)
+    result = {"epoch_ms": ms, "epoch_ms_device": ms_dev, "epochs_timed": n_timed, "rank_epoch_ms_device": [round(x, 5) for x in rank_ms],
+              "batches": len(it), "world": world, "grouped": grouped,
               "tile_bitmaps_used": bool(grouped and gmaps), "nonzero_tile_fraction": it.nonzero_tile_fraction() if it.tile_maps else None,
               "checksum": float(last.sum().item()) if last is not None else 0.0, "nodes_per_batch": int(np.mean(counts))}
     if args.cpu_baseline and rank == 0:
