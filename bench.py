@@ -520,18 +520,21 @@ def cpu_baseline_port(a_words, x_words_by_bit, budget_s=12.0):
 
 # --------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference arm.  The reference implements this path only in CUDA, so its own code path is
-    the extension rebuilt for sm_100a from the unmodified sources (oracle/_ref/QGTC_ref), called
-    through its public API (QGTC.bitMM2Bit on device tensors) on the same box; when that cannot be
-    loaded or --ref-device cpu is given, the oracle's C port is timed on the host cores instead."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    """The reference arm.  The reference implements this path only in CUDA, so its own code path is the extension rebuilt for
+    sm_100a from the unmodified sources (oracle/_ref/QGTC_ref), called through its public API (QGTC.bitMM2Bit on device tensors) on
+    the same box: same workload definition as the repo's arm (batches of G graphs x four bit widths, one rank per GPU, MAX over
+    ranks), one pass per step (a bounded sample: each of its calls costs milliseconds of host time, QGTC_device.cu:223-250).
+    It also prints the reference's kernel-only figure in its own convention (bitMM2Bit_profile) and a same-box reference epoch
+    (the logical-warp-index build, whose results are correct on a B200: oracle/ref_logical_warpid.h).  When the extension cannot
+    be loaded or --ref-device cpu is given, the oracle's C port is timed on the host cores instead (rank 0 only)."""
     import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    G = args.graphs
     line_common = {
         "impl": "reference", "metric": "bit-GEMM int TOPS (1/2/4/8-bit) vs INT8 peak; Cluster-GCN epoch ms @1-8 GPU",
-        "unit": "TOPS (2*M*K*N per GEMM)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+        "unit": "TOPS (2*M*K*N per GEMM)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": config_dict(G),
     }
     ref = None
     if args.ref_device in ("auto", "cuda"):
@@ -539,39 +542,39 @@ def run_reference(args):
             import torch
             import build_ref
             if torch.cuda.is_available():
-                torch.cuda.set_device(0)
                 ref = build_ref.load_variant("QGTC_ref")
         except Exception as e:
             ref = None
             if args.ref_device == "cuda":
-                print(json.dumps({"impl": "reference", "unavailable": "reference extension not loadable: %r" % (e,)}))
+                if rank == 0:
+                    print(json.dumps({"impl": "reference", "unavailable": "reference extension not loadable: %r" % (e,)}))
                 return
     if ref is not None:
         import torch
-        Gr = 8  # bounded sample of the workload: 8 graphs per bit width per step
-        gen = torch.Generator(device="cuda").manual_seed(3)
-        devnull = os.open(os.devnull, os.O_WRONLY)
+        rank, local, world = dist_setup(args.gpus)
+        gen = torch.Generator(device="cuda").manual_seed(3 + rank)
         A, X = [], {b: [] for b in BITS}
-        for g in range(Gr):
+        for g in range(G):
             A.append(ref.val2bit((torch.rand((M, K), device="cuda", generator=gen) < 0.5).float(), 1, False, False))
             for b in BITS:
                 X[b].append(ref.val2bit(torch.randint(0, 1 << b, (K, N), device="cuda", generator=gen).float(), b, True, False))
 
         def step():
             for b in BITS:
-                for g in range(Gr):
+                for g in range(G):
                     ref.bitMM2Bit(A[g], X[b][g], M, K, N, 1, b, b)
 
-        for _ in range(max(1, args.warmup)):
+        for _ in range(max(1, min(args.warmup, 2))):
             step()
-        torch.cuda.synchronize()
+        barrier(world)
         w0 = time.perf_counter()
         for _ in range(args.steps):
             step()
         torch.cuda.synchronize()
-        s = (time.perf_counter() - w0) / args.steps
-        os.close(devnull)
-        # kernel-only figure of the reference: its own bitMM2Bit_profile (200 back-to-back launches, prints TFLOPs)
+        barrier(world)
+        rank_s = gather_floats((time.perf_counter() - w0) / args.steps, world)
+        s = max(rank_s)
+        # kernel-only figures of the reference in its own convention: bitMM2Bit_profile (200 back-to-back launches, prints TFLOPs)
         kernel_only = {}
         try:
             import re
@@ -593,17 +596,47 @@ def run_reference(args):
                         kernel_only[str(b)] = float(m.group(1))
         except Exception as e:
             kernel_only = {"error": repr(e)[:200]}
-        val = OPS_PER_GEMM * Gr * len(BITS) / s / 1e12
-        line = dict(line_common)
-        line.update({"value": round(val, 3), "ms_per_step": round(s * 1e3, 3),
-                     "dtype": "b1 AND+popc (wmma m8n8k128; emulated with IMMA on sm_100a)",
-                     "config": {"workload": "BASELINE configs[1]: bit-GEMM 4096x4096x64, %d graphs x {1,2,4,8} bits per step, "
-                                            "reference QGTC.bitMM2Bit (unmodified sources rebuilt for sm_100a) on cuda:0" % Gr},
-                     "cpu_baseline": {"value": round(val, 3), "unit": "TOPS (2*M*K*N per GEMM)", "cores": 0, "kind": "reference",
-                                      "sample": "reference CUDA kernels on the same B200 (the reference has no CPU implementation of this path)"},
-                     "reference_kernel_only_tops": kernel_only,
-                     "e2e": {"value": round(val, 3), "unit": "TOPS (2*M*K*N per GEMM)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        del A, X
+        torch.cuda.empty_cache()
+        # same-box reference epoch: the reference's ops driven by this repo's mirror of main_qgtc.py (per-batch loop, eager),
+        # ppi-shaped synthetic graph, batches sharded over the ranks like the repo's arm
+        epoch = None
+        if not args.no_epoch:
+            try:
+                import build_ref as _br
+                from qgtc_ppopp22_b200 import cluster as C
+                from qgtc_ppopp22_b200 import main_qgtc as drv
+                ref_lw = _br.load_variant("QGTC_ref_lw")
+                g = C.make_synthetic_graph("ppi", 1500)
+                a = drv.build_parser().parse_args(["--dataset", "ppi", "--n-epochs", "3", "--bit_width", "2", "--use_QGTC", "--n-classes", "121"])
+                r = drv.run(a, graph=g, quiet=True, ops=ref_lw)
+                epoch = {"cluster_gcn_ppi_2bit": {"per_batch_eager_ms": round(r["epoch_ms"], 3), "epochs_timed": r["epochs_timed"],
+                                                  "ops": "oracle/_ref/QGTC_ref_lw (reference sources, logical warp index; results correct on B200)",
+                                                  "n_gpus": world}}
+            except Exception as e:
+                epoch = {"error": repr(e)[:300]}
+        if rank == 0:
+            val = OPS_PER_GEMM * G * len(BITS) * world / s / 1e12
+            line = dict(line_common)
+            line.update({"value": round(val, 3), "ms_per_step": round(s * 1e3, 3),
+                         "dtype": "b1 AND+popc (wmma m8n8k128; emulated with IMMA on sm_100a)",
+                         "step_definition": "one pass over the batch of %d graphs at each of the four bit widths through QGTC.bitMM2Bit of the "
+                                            "unmodified reference rebuilt for sm_100a, one process per GPU" % G,
+                         "rank_s_per_step": stats(rank_s) if world > 1 else None,
+                         "cpu_baseline": {"value": round(val, 3), "unit": "TOPS (2*M*K*N per GEMM)", "cores": 0, "kind": "reference",
+                                          "sample": "reference CUDA kernels on the same B200s, one pass (%d graphs x 4 bit widths) per step "
+                                                    "(the reference has no CPU implementation of this path)" % G},
+                         "profile_convention_tops": kernel_only,
+                         "single_gemm_per_launch_tops": kernel_only,
+                         "reference_kernel_only_tops": kernel_only,
+                         "epochs": epoch,
+                         "e2e": {"value": round(val, 3), "unit": "TOPS (2*M*K*N per GEMM)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            print(json.dumps(line))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    if rank != 0:
         return
     # CPU port
     import c_oracle
@@ -623,8 +656,8 @@ def run_reference(args):
     s = (time.perf_counter() - w0) / args.steps
     val = OPS_PER_GEMM * len(BITS) / s / 1e12
     line = dict(line_common)
-    line.update({"value": round(val, 4), "ms_per_step": round(s * 1e3, 3), "dtype": "b1 AND+popcount (uint64)",
-                 "config": {"workload": "BASELINE configs[1]: bit-GEMM 4096x4096x64, one graph x {1,2,4,8} bits per step, oracle C port on host cores"},
+    line.update({"value": round(val, 4), "ms_per_step": round(s * 1e3, 3), "dtype": "b1 AND+popcount (uint64)", "n_gpus": 1,
+                 "step_definition": "one graph x {1,2,4,8} bits per step, oracle C port on the host cores",
                  "cpu_baseline": {"value": round(val, 4), "unit": "TOPS (2*M*K*N per GEMM)", "cores": c_oracle.num_threads(), "kind": "port",
                                   "sample": "one 4096x4096x64 GEMM per bit width per step"},
                  "e2e": {"value": round(val, 4), "unit": "TOPS (2*M*K*N per GEMM)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})

@@ -107,7 +107,7 @@ static int run_grouped_single(const GemmArgs& a, int epi, cudaStream_t st) {
 // QGTC_ENGINE_AUTO, single problems: the batch engine (gemm_tc05.cu: TMA-fed, feature image built by a separate prep
 // kernel, 4-bit operand path) wins on large problems, the grouped engine (one launch, in-kernel conversion) on small ones
 static double auto_batch_engine_min_ops() {
-    static const double v = [] { const char* e = std::getenv("QGTC_AUTO_BATCH_MIN_OPS"); return e ? std::atof(e) : 6.0e9; }();
+    static const double v = [] { const char* e = std::getenv("QGTC_AUTO_BATCH_MIN_OPS"); return e ? std::atof(e) : 1.0e8; }();   // measured: profiles/r2_single_call_call6.txt
     return v;
 }
 

@@ -46,7 +46,7 @@ constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kIssuerWarp = kConvWarp0 + kConvWarps;
 constexpr int kThreads = (kIssuerWarp + 1) * 32;   // 544
 constexpr int kARing = 3;                     // staged pipeline items per expander warp (cp.async groups in flight)
-constexpr int kBRing = 2;                     // ... per converter thread
+constexpr int kMaxBRing = 4;                  // ... per converter thread: 2..4 by shared-memory budget (GrpArgs::b_ring)
 constexpr int kMaxTasks = 2;                  // (chunk, column) conversion tasks per converter thread and item: cps * NP <= 256
 constexpr int kMaxStagesG = 4;
 constexpr int kMaxCpsG = 4;
@@ -71,7 +71,7 @@ struct GrpArgs {
     int count, units;
     int N, NP, bit1, bit2, out_bit, epi, pad128;
     int cps, stages, dbufs, groups;           // chunks per item, A/B ring depth, accumulator buffers, expander groups in use
-    int a_slot_bytes, b_slot_bytes, b_stage_bytes;
+    int a_slot_bytes, b_slot_bytes, b_stage_bytes, b_ring, max_nst, mode2;
     int off_bstage, off_bring, off_bars, off_flags, off_misc, off_units;   // shared-memory offsets from the 1024-byte aligned base
     unsigned int cps_inv;
     unsigned flags;
@@ -149,6 +149,59 @@ __device__ __forceinline__ int walk_bitmap_stages(const uint32_t* bm, int gdk, i
         }                                                                                                   \
     } while (0)
 
+// Re-assemble NB bit planes of one 128-bit K chunk into 32 registers of four u8 values: byte i of r[8 s + c] = value of K
+// element 32 s + c + 8 i = sum over planes of bit (c + 8 i) of the plane's word s, moved to bit p (the K permutation of
+// gemm_tc05.cu: a register is a mask of the packed word).  Plane p's 16 bytes are at src + p * stride.  With the plane
+// index known at compile time every (plane, register) step is one shift and one AND-OR.  Returns the OR of all words.
+// SCALED (the B operand in expansion mode 2, see the expanders): element of column c additionally carries 2^(3 - c % 4).
+template <int NB, bool SCALED>
+__device__ __forceinline__ uint32_t assemble_planes(const unsigned char* src, int stride, uint32_t (&r)[32]) {
+    uint32_t any = 0u;
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+        const uint4 pv = *reinterpret_cast<const uint4*>(src + p * stride);
+        const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+        any |= pv.x | pv.y | pv.z | pv.w;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int to = p + (SCALED ? 3 - (c & 3) : 0);     // compile-time after unrolling; <= 7 (SCALED needs NB <= 5)
+                const uint32_t sh = c >= to ? (w[ks] >> (c - to)) : (w[ks] << (to - c));
+                const uint32_t v = sh & (0x01010101u << to);
+                r[ks * 8 + c] = p == 0 ? v : (r[ks * 8 + c] | v);
+            }
+        }
+    }
+    return any;
+}
+// any plane count (1..8): the common widths unrolled, the rest through a runtime plane loop
+template <bool SCALED>
+__device__ __forceinline__ uint32_t assemble_planes_rt(int nb, const unsigned char* src, int stride, uint32_t (&r)[32]) {
+    switch (nb) {
+        case 1: return assemble_planes<1, SCALED>(src, stride, r);
+        case 2: return assemble_planes<2, SCALED>(src, stride, r);
+        case 4: return assemble_planes<4, SCALED>(src, stride, r);
+        case 8: if (!SCALED) return assemble_planes<8, false>(src, stride, r); break;
+        default: break;
+    }
+    uint32_t any = 0u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) r[e] = 0u;
+#pragma unroll 1
+    for (int p = 0; p < nb; ++p) {
+        const uint4 pv = *reinterpret_cast<const uint4*>(src + p * stride);
+        const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+        any |= pv.x | pv.y | pv.z | pv.w;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) r[ks * 8 + c] |= ((w[ks] >> c) & 0x01010101u) << (p + (SCALED ? 3 - (c & 3) : 0));
+        }
+    }
+    return any;
+}
+
 // fast path first: a plain try_wait (already-complete phases return at once), then the bounded suspending wait
 __device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity, unsigned int* ef, int where) {
     if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity, ef, where, true);
@@ -164,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 
     unsigned char* a_rings = smem;                                   // [kExpWarps][kARing][a_slot_bytes]
     unsigned char* b_stages = smem + T.off_bstage;                   // [S][cps * NP * 128]
-    unsigned char* b_ring = smem + T.off_bring;                      // [kBRing][b_slot_bytes]
+    unsigned char* b_ring = smem + T.off_bring;                      // [T.b_ring][b_slot_bytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.off_bars);
     uint64_t* full = bars;                         // [kMaxStagesG] 4 expander warps + kConvWarps converter warps -> MMA
     uint64_t* empty = bars + kMaxStagesG;          // [kMaxStagesG] MMA commit -> expanders, converters
@@ -196,7 +249,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 
     // ---- work lists (kernel parameters only: nothing here depends on the previous kernel, so it runs before the wait below)
     const int units_here = (T.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    ItemRec* items = reinterpret_cast<ItemRec*>(smem + T.off_units + units_here * (int)sizeof(UnitRec));
+    const int units_cap = (T.units + (int)gridDim.x - 1) / (int)gridDim.x;       // the launcher sized the lists for this many units per CTA
+    ItemRec* items = reinterpret_cast<ItemRec*>(smem + T.off_units + units_cap * (int)sizeof(UnitRec));
+    unsigned char* reuse_flag = reinterpret_cast<unsigned char*>(items + units_cap * T.max_nst);
     for (int k = threadIdx.x; k < units_here; k += kThreads) {
         const int u = (int)blockIdx.x + k * (int)gridDim.x;
         int z;
@@ -270,6 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     const int dcols = T.dbufs * NP;                // accumulators first, then the A stages
     const int stage_cols = CPS * 32;
     const bool nojump = (T.flags & QGTC_FLAG_NO_ZERO_JUMP) != 0;
+    const bool mode2 = A1 && T.mode2 != 0;         // launcher: bit2 <= 5 and 8 x the largest possible sum fits an int32
+    const int dshift = mode2 ? 3 : 0;
     unsigned int* const ef = T.error_flag;
 
     if (warp < kExpWarps) {
@@ -326,31 +383,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 for (int j = 0; j < nch; ++j) {
                     uint32_t r[32];
                     uint32_t any;
-                    if (A1) {
+                    if (A1 && mode2) {
+                        // expansion mode 2 (gemm_tc05.cu): bit c of every byte stays where it is inside its nibble -- one AND per
+                        // register, one shift per word -- so A holds 2^(c % 4); the converters scale the B rows by 2^(3 - c % 4)
+                        // and the accumulators hold 8 x the sums (the epilogue shifts them back, exactly)
                         const uint4 pv = *reinterpret_cast<const uint4*>(src + j * 512);
                         const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
                         any = pv.x | pv.y | pv.z | pv.w;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            r[ks * 8] = w[ks] & 0x01010101u;
+                            const uint32_t hi = w[ks] >> 4;
 #pragma unroll
-                            for (int c = 1; c < 8; ++c) r[ks * 8 + c] = (w[ks] >> c) & 0x01010101u;
-                        }
-                    } else {
-                        any = 0u;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) r[e] = 0u;
-#pragma unroll 1
-                        for (int p = 0; p < T.bit1; ++p) {
-                            const uint4 pv = *reinterpret_cast<const uint4*>(src + (p * CPS + j) * 512);
-                            const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-                            any |= pv.x | pv.y | pv.z | pv.w;
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) r[ks * 8 + c] |= ((w[ks] >> c) & 0x01010101u) << p;
+                            for (int c = 0; c < 4; ++c) {
+                                r[ks * 8 + c] = w[ks] & (0x01010101u << c);
+                                r[ks * 8 + 4 + c] = hi & (0x01010101u << c);
                             }
                         }
+                    } else {
+                        any = A1 ? assemble_planes<1, false>(src + j * 512, 0, r) : assemble_planes_rt<false>(T.bit1, src + j * 512, CPS * 512, r);
                     }
                     if (nojump || __any_sync(0xffffffffu, any != 0u)) nzmask |= 1u << j;
                     if (j == 0) {   // the first chunk is expanded before the wait: only the store sits behind it
@@ -386,67 +436,83 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             tj[i] = task / NP;
             tn_[i] = task - tj[i] * NP;
         }
+        // Stage re-use (one byte per item, written and read by the converters only): an item whose B chunk is identical to those of the S
+        // items before it -- the weight products, where every unit multiplies with the same W -- finds its stage already
+        // holding the converted image: the converters neither load nor convert anything for it.
+        for (int it = t; it < n_items; it += kConvThreads) {
+            bool same = it >= S;
+            const ItemRec I = items[it];
+            const UnitRec& U = units[I.unit];
+            for (int d = 1; same && d <= S; ++d) {
+                const ItemRec J = items[it - d];
+                const UnitRec& V = units[J.unit];
+                same = J.c0 == I.c0 && J.nch == I.nch && V.x2 == U.x2 && V.x2_words == U.x2_words && V.gdk == U.gdk;
+            }
+            reuse_flag[it] = same ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kConvThreads) : "memory");     // the four converter warps only
         unsigned char* ring = b_ring + t * 16;                         // piece (i, plane) of this thread at + (i * bit2 + plane) * 2048
         const bool tr = TRACE && warp == kConvWarp0 && tlane;
         if (tr) QGTC_GTRACE(2, 20);
+        const int RB = T.b_ring;                                       // staged items in flight (2..4, by shared-memory budget)
         int s = 0, slot_l = 0, slot_c = 0;
         uint32_t use = 0;
 #pragma unroll 1
-        for (int it_c = -(kBRing - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
+        for (int it_c = -(RB - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
             if (it_l < n_items) {
                 const ItemRec I = items[it_l];
-                const UnitRec& U = units[I.unit];
-                const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
-                const unsigned long long w_offset = gdk4 * (unsigned long long)pn;
-                unsigned char* dst = ring + slot_l * T.b_slot_bytes;
+                if (!reuse_flag[it_l]) {     // not a stage re-use: stage this item's packed words
+                    const UnitRec& U = units[I.unit];
+                    const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
+                    const unsigned long long w_offset = gdk4 * (unsigned long long)pn;
+                    unsigned char* dst = ring + slot_l * T.b_slot_bytes;
 #pragma unroll
-                for (int i = 0; i < kMaxTasks; ++i) {
-                    if (tj[i] < I.nch) {
-                        const unsigned long long idx0 = (unsigned long long)tn_[i] * gdk4 + 4ull * (I.c0 + tj[i]);
-                        const bool col_ok = tn_[i] < p8n;
-                        for (int qq = 0; qq < T.bit2; ++qq) {
-                            const unsigned long long idx = idx0 + (unsigned long long)qq * w_offset;
-                            const int nb = col_ok ? piece_bytes(idx, U.x2_words) : 0;
-                            cp_async16_zfill(dst + (i * T.bit2 + qq) * (kConvThreads * 16), nb ? (const void*)(U.x2 + idx) : (const void*)U.x2, nb);
+                    for (int i = 0; i < kMaxTasks; ++i) {
+                        if (tj[i] < I.nch) {
+                            const unsigned long long idx0 = (unsigned long long)tn_[i] * gdk4 + 4ull * (I.c0 + tj[i]);
+                            const bool col_ok = tn_[i] < p8n;
+                            for (int qq = 0; qq < T.bit2; ++qq) {
+                                const unsigned long long idx = idx0 + (unsigned long long)qq * w_offset;
+                                const int nb = col_ok ? piece_bytes(idx, U.x2_words) : 0;
+                                cp_async16_zfill(dst + (i * T.bit2 + qq) * (kConvThreads * 16), nb ? (const void*)(U.x2 + idx) : (const void*)U.x2, nb);
+                            }
                         }
                     }
+                    if (++slot_l == RB) slot_l = 0;
                 }
-                if (++slot_l == kBRing) slot_l = 0;
             }
             cp_async_commit();
             if (it_c < 0) continue;
-            cp_async_wait<kBRing - 1>();
-            if (tr) QGTC_GTRACE(2, 22);
-            const int nch = items[it_c].nch;
-            gwait(&empty[s], (use & 1) ^ 1, ef, 2);                    // the MMAs that read this stage's previous content are done
-            if (tr) QGTC_GTRACE(2, 23);
-            const unsigned char* src = ring + slot_c * T.b_slot_bytes;
-            if (++slot_c == kBRing) slot_c = 0;
-            unsigned char* stage = b_stages + (size_t)s * T.b_stage_bytes;
-#pragma unroll
-            for (int i = 0; i < kMaxTasks; ++i) {
-                if (tj[i] >= nch) continue;
-                uint32_t o[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) o[e] = 0u;
-#pragma unroll 1
-                for (int qq = 0; qq < T.bit2; ++qq) {
-                    const uint4 pv = *reinterpret_cast<const uint4*>(src + (i * T.bit2 + qq) * (kConvThreads * 16));
-                    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
-                    // byte i of o[8 s + c] = value of K element 32 s + c + 8 i (the expanders' K permutation)
-#pragma unroll
-                    for (int sdx = 0; sdx < 4; ++sdx) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) o[sdx * 8 + c] |= ((w[sdx] >> c) & 0x01010101u) << qq;
-                    }
-                }
-                // image of one K chunk: [k group (8)][column block][8 columns][16 B]; k group kg = registers 4 kg .. 4 kg + 3
-                unsigned char* dstc = stage + (size_t)tj[i] * NP * 128 + (size_t)(tn_[i] >> 3) * 128 + (tn_[i] & 7) * 16;
-#pragma unroll
-                for (int kg = 0; kg < 8; ++kg)
-                    *reinterpret_cast<uint4*>(dstc + (size_t)kg * (NP / 8) * 128) = make_uint4(o[4 * kg], o[4 * kg + 1], o[4 * kg + 2], o[4 * kg + 3]);
+            const ItemRec I = items[it_c];
+            const bool reuse = reuse_flag[it_c] != 0;
+            if (!reuse) {
+                if (RB == 4) cp_async_wait<3>();
+                else if (RB == 3) cp_async_wait<2>();
+                else cp_async_wait<1>();
             }
-            fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+            if (tr) QGTC_GTRACE(2, 22);
+            const int nch = I.nch;
+            // the MMAs that read this stage's previous content are done (also orders this arrival after the stage's previous phase)
+            gwait(&empty[s], (use & 1) ^ 1, ef, 2);
+            if (tr) QGTC_GTRACE(2, 23);
+            if (!reuse) {
+                const unsigned char* src = ring + slot_c * T.b_slot_bytes;
+                if (++slot_c == RB) slot_c = 0;
+                unsigned char* stage = b_stages + (size_t)s * T.b_stage_bytes;
+#pragma unroll
+                for (int i = 0; i < kMaxTasks; ++i) {
+                    if (tj[i] >= nch) continue;
+                    uint32_t o[32];
+                    if (A1 && mode2) assemble_planes_rt<true>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
+                    else assemble_planes_rt<false>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
+                    // image of one K chunk: [k group (8)][column block][8 columns][16 B]; k group kg = registers 4 kg .. 4 kg + 3
+                    unsigned char* dstc = stage + (size_t)tj[i] * NP * 128 + (size_t)(tn_[i] >> 3) * 128 + (tn_[i] & 7) * 16;
+#pragma unroll
+                    for (int kg = 0; kg < 8; ++kg)
+                        *reinterpret_cast<uint4*>(dstc + (size_t)kg * (NP / 8) * 128) = make_uint4(o[4 * kg], o[4 * kg + 1], o[4 * kg + 2], o[4 * kg + 3]);
+                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (tr) QGTC_GTRACE(2, 24);
@@ -531,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int n = 16 * cb + j;
-                            if (n < N) out[(size_t)m * N + n] = (float)v[j];
+                            if (n < N) out[(size_t)m * N + n] = (float)(v[j] >> dshift);
                         }
                     }
                 }
@@ -542,13 +608,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 const bool row_ok = m < p8(M);
                 const uint32_t rmask = m < M ? 0xffffffffu : 0u;
                 uint32_t* out_row = out + (unsigned long long)m * wpr;
-#define QGTC_GRP_EPI(OBV) epi_bits_tile<OBV, false, false, false, 1>(d_tmem, NP, 0, N, ob, 0, rmask, row_ok, out_row, opt_offset)
-                switch (ob) {
-                    case 1: QGTC_GRP_EPI(1); break;
-                    case 2: QGTC_GRP_EPI(2); break;
-                    case 4: QGTC_GRP_EPI(4); break;
-                    case 8: QGTC_GRP_EPI(8); break;
-                    default: QGTC_GRP_EPI(0); break;
+#define QGTC_GRP_EPI(OBV, NNV, FASTV) epi_bits_tile<OBV, NNV, FASTV, false, 1>(d_tmem, NP, 0, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
+                if (mode2) {   // 8 x sums, non-negative: byte-parallel requantize up to 4 output bits
+                    switch (ob) {
+                        case 1: QGTC_GRP_EPI(1, true, true); break;
+                        case 2: QGTC_GRP_EPI(2, true, true); break;
+                        case 4: QGTC_GRP_EPI(4, true, true); break;
+                        case 8: QGTC_GRP_EPI(8, true, false); break;
+                        default: if (ob <= 4) QGTC_GRP_EPI(0, true, true); else QGTC_GRP_EPI(0, true, false); break;
+                    }
+                } else {
+                    switch (ob) {
+                        case 1: QGTC_GRP_EPI(1, false, false); break;
+                        case 2: QGTC_GRP_EPI(2, false, false); break;
+                        case 4: QGTC_GRP_EPI(4, false, false); break;
+                        case 8: QGTC_GRP_EPI(8, false, false); break;
+                        default: QGTC_GRP_EPI(0, false, false); break;
+                    }
                 }
 #undef QGTC_GRP_EPI
                 if (row_ok) {   // zero pad words of the row (output buffers are not pre-zeroed)
@@ -572,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int n = 16 * cb + j;
-                            const uint32_t val = (m < M && n < N) ? ((uint32_t)requant(v[j], ob) & keep) : 0u;
+                            const uint32_t val = (m < M && n < N) ? ((uint32_t)requant(v[j] >> dshift, ob) & keep) : 0u;
                             for (int p = 0; p < ob; ++p) {
                                 const uint32_t word = __brev(__ballot_sync(0xffffffffu, (val >> p) & 1u));
                                 if (lane == ((j + p) & 31)) out[(unsigned long long)p * plane + (unsigned long long)n * kw + mw] = word;
@@ -601,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 }
 
 struct GrpPlan {
-    int NP, cps, stages, dbufs, groups, a_slot, b_slot, b_stage, off_bstage, off_bring, off_bars, off_flags, off_misc, off_units, smem_total;
+    int NP, cps, stages, dbufs, groups, a_slot, b_slot, b_stage, b_ring, off_bstage, off_bring, off_bars, off_flags, off_misc, off_units, smem_total;
 };
 
 // pipeline geometry for (N, bit1, bit2); false when the shape does not fit this engine
@@ -619,14 +695,19 @@ bool plan_for(int N, int bit1, int bit2, GrpPlan& pl) {
         pl.stages = stages;
         pl.groups = stages < 2 ? 1 : 2;          // G <= S keeps the parity-only mbarrier waits unambiguous (see gemm_tc05.cu)
         pl.a_slot = bit1 * cps * 512;
-        pl.b_slot = kMaxTasks * bit2 * kConvThreads * 16;
+        const int tasks_per_thread = (cps * pl.NP + kConvThreads - 1) / kConvThreads;      // 1 or 2 (cps * NP <= 256)
+        pl.b_slot = tasks_per_thread * bit2 * kConvThreads * 16;
         pl.b_stage = cps * pl.NP * 128;
         int off = kExpWarps * kARing * pl.a_slot;
         off = (off + 1023) & ~1023;
         pl.off_bstage = off;
         off += stages * pl.b_stage;
         pl.off_bring = off;
-        off += kBRing * pl.b_slot;
+        // converter staging ring: as deep as shared memory allows (the converters' loads are issued b_ring - 1 items ahead;
+        // two is not enough to cover the L2 / HBM latency of a short item), leaving room for the per-CTA work lists
+        pl.b_ring = kMaxBRing;
+        while (pl.b_ring > 2 && off + pl.b_ring * pl.b_slot + 512 + 24 * 1024 > 227 * 1024) --pl.b_ring;
+        off += pl.b_ring * pl.b_slot;
         pl.off_bars = off;
         off += (2 * kMaxStagesG + 4) * 8;
         pl.off_flags = off;
@@ -677,7 +758,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
     while (first < count) {
         // as many problems as the parameter table and the per-CTA work lists hold
         long long units = 0;
-        int n = 0, max_nst = 1;
+        int n = 0, max_nst = 1, max_gdk = 1;
         while (first + n < count && n < limit) {
             const GroupedProblemHost& h = probs[first + n];
             const long long u = (p8(h.M) + 127) / 128;
@@ -693,13 +774,14 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
                 for (long long k = 0; k < u; ++k) T.unit_z[units + k] = (unsigned short)n;
             const int nst = (s128(h.K) + pl.cps - 1) / pl.cps;
             if (nst > max_nst) max_nst = nst;
+            if (s128(h.K) > max_gdk) max_gdk = s128(h.K);
             units += u;
             ++n;
         }
         {
             const long long grid_ = units < kNumSMs ? units : kNumSMs;
             const long long upc = (units + grid_ - 1) / grid_;
-            const long long lists = upc * (long long)sizeof(UnitRec) + upc * max_nst * (long long)sizeof(ItemRec);
+            const long long lists = upc * (long long)sizeof(UnitRec) + upc * max_nst * (long long)(sizeof(ItemRec) + 1);
             if (pl.smem_total + lists > 227 * 1024) {
                 if (n <= 1) return QGTC_ERR_UNSUPPORTED;
                 limit = n / 2;
@@ -710,7 +792,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         T.units = (int)units;
         T.N = N; T.NP = pl.NP; T.bit1 = bit1; T.bit2 = bit2; T.out_bit = out_bit; T.epi = epi; T.pad128 = pad128;
         T.cps = pl.cps; T.stages = pl.stages; T.dbufs = pl.dbufs; T.groups = pl.groups;
-        T.a_slot_bytes = pl.a_slot; T.b_slot_bytes = pl.b_slot; T.b_stage_bytes = pl.b_stage;
+        T.a_slot_bytes = pl.a_slot; T.b_slot_bytes = pl.b_slot; T.b_stage_bytes = pl.b_stage; T.b_ring = pl.b_ring;
         T.off_bstage = pl.off_bstage; T.off_bring = pl.off_bring; T.off_bars = pl.off_bars; T.off_flags = pl.off_flags; T.off_misc = pl.off_misc;
         T.off_units = pl.off_units;
         T.cps_inv = pl.cps == 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)pl.cps - 1ull) / (unsigned long long)pl.cps);
@@ -720,7 +802,13 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         if (g_grp_trace) cudaMemsetAsync(g_grp_trace, 0, kGrpTraceWords * 8, st);
         const int grid = T.units < kNumSMs ? T.units : kNumSMs;
         const int units_per_cta = (T.units + grid - 1) / grid;
-        const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * (int)sizeof(ItemRec);
+        const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * ((int)sizeof(ItemRec) + 1);
+        T.max_nst = max_nst;
+        {   // expansion mode 2 (1-bit A only): the 8 x scaled sums must fit an int32 and the scaled features a byte
+            static const bool no_mode2 = [] { const char* e = getenv("QGTC_GRP_MODE2"); return e && e[0] == '0'; }();
+            const double max_sum = (double)max_gdk * 128.0 * (double)((1u << bit2) - 1u);
+            T.mode2 = (!no_mode2 && bit1 == 1 && bit2 <= 5 && max_sum * 8.0 < 2147483648.0) ? 1 : 0;
+        }
         auto launch = [&](auto kfn) -> int {
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return record_cuda_error(e, "cudaFuncSetAttribute(gemm_grp)");

@@ -164,6 +164,27 @@ def test_grouped_many_problems_and_repeats(capi, coracle):
         assert not bad, bad[:10]
 
 
+@pytest.mark.parametrize("b,K,N", [(2, 50, 16), (4, 128, 121), (1, 300, 64), (8, 16, 16)])
+def test_grouped_shared_weights_stage_reuse(capi, coracle, b, K, N):
+    """The weight products of an epoch (X.W, o.W: every problem multiplies with the same packed W, K of one or a few chunks):
+    the converters re-use a stage that already holds the converted chunk.  Hundreds of units per launch so that every CTA
+    runs through several of them; a second weight matrix is interleaved so that runs of identical chunks start and stop."""
+    rng = np.random.default_rng(b * 100 + K)
+    Wa = coracle.val2bit(rand_features(rng, (K, N), b), b, True, False)
+    Wb = coracle.val2bit(rand_features(rng, (K, N), b), b, True, False)
+    dWa, dWb = dev_words(Wa), dev_words(Wb)
+    pool = []
+    for M in (759, 128, 300, 1, 515):
+        x = coracle.val2bit(rand_features(rng, (M, K), b), b, False, False)
+        pool.append((M, dev_words(x), {0: dev_words(coracle.bitMM2Bit(x, Wa, M, K, N, b, b, b)), 1: dev_words(coracle.bitMM2Bit(x, Wb, M, K, N, b, b, b))}))
+    picks = [(pool[int(i)], int(w)) for i, w in zip(rng.integers(0, len(pool), size=220), (rng.random(220) < 0.15))]
+    outs = capi.bitmm_grouped([p[0][1] for p in picks], [dWb if p[1] else dWa for p in picks], [p[0][0] for p in picks], [K] * len(picks),
+                              N, b, b, b, engine=capi.ENGINE_GROUPED)
+    torch.cuda.synchronize()
+    bad = [i for i, (o, p) in enumerate(zip(outs, picks)) if not torch.equal(o, p[0][2][p[1]])]
+    assert not bad, bad[:10]
+
+
 def _chain_specs(kind, n, D, h, C, b):
     """(A operand, B operand, K, N, bit1, float?) per op; names refer to the running values of the chain."""
     if kind == "gcn":       # main_qgtc.py:146-154
