@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-epoch", action="store_true", help="skip the Cluster-GCN epoch block")
+    ap.add_argument("--no-zero-tile", action="store_true", help="skip the zero-tile-jumping / adjacency-size block (BASELINE configs[4])")
     return ap.parse_args()
 
 
@@ -403,6 +404,15 @@ def run_ours(args):
         except Exception as e:  # the headline metric must still be printed
             epoch = {"error": repr(e)[:300]}
 
+    zero_tiles = None
+    if rank == 0 and world == 1 and not args.no_zero_tile:
+        try:
+            del A, X, outs
+            torch.cuda.empty_cache()
+            zero_tiles = zero_tile_block()
+        except Exception as e:
+            zero_tiles = {"error": repr(e)[:300]}
+
     if rank == 0:
         cfg = config_dict(G)
         cfg.update({"engine": args.engine, "passes_per_step": P,
@@ -437,6 +447,7 @@ def run_ours(args):
                                  "not by the tensor pipe (limiter fields)" % peaks["source"]},
             "cpu_baseline": cpu,
             "epochs": epoch,
+            "zero_tile_sweep": zero_tiles,
             "clocks": clocks,
             "parity_spot_check": ok,
         }
@@ -444,6 +455,64 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def zero_tile_block():
+    """BASELINE configs[4] (Fig. 8b / 9): zero-tile jumping and adjacency-size sweep.  Synthetic adjacencies at partition sizes
+    1K-16K -- i.i.d. density p and block-diagonal (128-node blocks, what a batch of small graphs looks like) -- times 64-wide 2-bit
+    features, batches of G graphs.  Per case: dense-equivalent TOPS (2*M*K*N) without jumping, with on-the-fly jumping and with
+    the precomputed tile bitmap; processed / total tiles as parse_counter.py:16 reports it (8 x 128-bit tiles of the reference's
+    counters, and the 128 x 128 tiles the tensor core consumes); and a bit-exact check of graph 0 against the C oracle."""
+    import numpy as np
+    import torch
+    import c_oracle
+    from qgtc_ppopp22_b200 import capi
+    Nz, b = 64, 2
+    gen = torch.Generator(device="cuda").manual_seed(3)
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        return event_timed(fn, reps)
+
+    rows = []
+    for Mz in (1024, 4096, 16384):
+        G = max(2, min(64, (256 << 20) // (Mz * Mz // 8)))
+        X = torch.stack([capi.val2bit(torch.randint(0, 4, (Mz, Nz), device="cuda", generator=gen).float(), b, True, False).view(-1) for _ in range(G)])
+        for kind, p in (("iid", 1.0), ("iid", 1e-2), ("iid", 1e-4), ("blockdiag128", 0.5)):
+            adj = []
+            for _ in range(G):
+                if kind == "iid":
+                    a = (torch.rand((Mz, Mz), device="cuda", generator=gen) < p).float()
+                else:
+                    a = torch.zeros((Mz, Mz), device="cuda")
+                    blk = (torch.rand((Mz // 128, 128, 128), device="cuda", generator=gen) < p).float()
+                    idx = torch.arange(Mz, device="cuda").view(Mz // 128, 128)
+                    for k in range(Mz // 128):
+                        a[idx[k][:, None], idx[k][None, :]] = blk[k]
+                adj.append(capi.val2bit(a, 1, False, False).view(-1))
+                del a
+            A = torch.stack(adj)
+            del adj
+            total, nz = capi.tile_counts(A[0].view(capi.packed_shape(capi.LAYOUT_ROW, 1, Mz, Mz)), Mz, Mz, Nz, 1, b)
+            bm = capi.tile_bitmap(A, Mz, Mz, G)
+            out = torch.empty((G, capi.packed_words(capi.LAYOUT_ROW, b, Mz, Nz)), dtype=torch.int32, device="cuda")
+            ops = 2.0 * Mz * Mz * Nz * G
+            r = {"M": Mz, "K": Mz, "N": Nz, "bits": b, "pattern": kind, "density": p, "graphs": G,
+                 "processed_over_total_tiles_8x128": round(nz / total, 4),
+                 "processed_over_total_tiles_128x128": round(float(((bm.view(-1).cpu().numpy().view(np.uint32)[:, None] >> np.arange(32, dtype=np.uint32)) & 1).sum())
+                                                             / (G * ((Mz + 127) // 128) ** 2), 4)}
+            ms = timed(lambda: capi.bitMM2Bit_batched(A, X, G, Mz, Mz, Nz, 1, b, b, out=out, flags=capi.FLAG_NO_ZERO_JUMP))
+            r["tops_no_jump"] = round(ops / (ms * 1e-3) / 1e12, 1)
+            ms = timed(lambda: capi.bitMM2Bit_batched(A, X, G, Mz, Mz, Nz, 1, b, b, out=out))
+            r["tops_jump_on_the_fly"] = round(ops / (ms * 1e-3) / 1e12, 1)
+            ms = timed(lambda: capi.bitMM2Bit_tilemap(A, X, bm, G, Mz, Mz, Nz, b, b, out=out))
+            r["tops_jump_tile_bitmap"] = round(ops / (ms * 1e-3) / 1e12, 1)
+            want = c_oracle.bitMM2Bit(A[0].cpu().numpy(), X[0].cpu().numpy(), Mz, Mz, Nz, 1, b, b).reshape(-1)
+            r["graph0_matches_oracle"] = bool(np.array_equal(out[0].cpu().numpy().view(np.uint32), want))
+            rows.append(r)
+            del A, bm, out
+    return rows
 
 
 def _epoch_args(drv, dataset, bits, extra, classes, hidden=16):

@@ -227,3 +227,37 @@ def shard_batches(costs, world_size: int):
         shards[r].append(i)
         loads[r] += costs[i]
     return [sorted(s) for s in shards]
+
+
+def gather_logits(per_batch, batch_ids, row_counts, world: int):
+    """All ranks' per-batch logits -> the full list ordered by batch id, on every rank (the only data collective of
+    the multi-GPU path, after the forward; NCCL over NVLink on GPUs, gloo in the CPU tests).
+    per_batch: this rank's float32 [n_i, C] tensors, batch_ids: their global ids, row_counts: rows of EVERY batch (known to
+    all ranks from the partition list).  Ranks pad their concatenated logits to the largest shard and all_gather once."""
+    if world == 1:
+        order = sorted(range(len(batch_ids)), key=lambda i: batch_ids[i])
+        return [per_batch[i] for i in order]
+    import torch.distributed as dist
+    C_ = per_batch[0].shape[1] if per_batch else 0
+    meta = torch.zeros(2, dtype=torch.int64)
+    meta[0], meta[1] = sum(int(t.shape[0]) for t in per_batch), C_
+    dev = per_batch[0].device if per_batch else torch.device("cpu")
+    metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(metas, meta.to(dev))
+    rows_max = max(int(m[0]) for m in metas)
+    C_ = max(int(m[1]) for m in metas)
+    mine = torch.zeros((rows_max, C_), dtype=torch.float32, device=dev)
+    if per_batch:
+        mine[:int(meta[0])] = torch.cat(list(per_batch), dim=0)
+    ids = torch.full((len(row_counts),), -1, dtype=torch.int64, device=dev)     # owner rank of every batch
+    ids[torch.as_tensor(list(batch_ids), dtype=torch.int64, device=dev)] = dist.get_rank()
+    owners = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(owners, ids)
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine)
+    out, cursor = [None] * len(row_counts), [0] * world
+    for b in range(len(row_counts)):
+        r = next(k for k in range(world) if int(owners[k][b]) == k)
+        out[b] = bufs[r][cursor[r]:cursor[r] + row_counts[b]]
+        cursor[r] += row_counts[b]
+    return out

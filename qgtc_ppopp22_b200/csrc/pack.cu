@@ -10,80 +10,68 @@ namespace qgtc {
 
 // ------------------------------------------------------------------------------------------
 // ROW layout: word [p][r][w] holds columns 32w..32w+31 of row r, MSB-first.
-// One warp handles (row, 128-column group) units: lane l owns columns 4l..4l+3 (one float4),
-// turns them into one nibble per plane, and an 8-lane OR-butterfly assembles the four words.
+// A lane owns one output word = 32 consecutive columns = one 128-byte line of the fp32 row (eight 16-byte loads, all in
+// flight together); a warp covers 1024 columns of a row per unit and stores 32 consecutive words per plane (one coalesced
+// 128-byte store per plane).  No shuffles, no float->int conversions: the quantizer rounds with a magic-number add
+// (quantize_bits), the plane words come from multiply-gathers (up to 3 planes) or 8 x 8 bit transposes (4 planes and up).
 // ------------------------------------------------------------------------------------------
-constexpr int kPackUnroll = 4;
-
-// Work decomposition without divisions in the loop: `splits` warps share a row (each takes a contiguous
-// range of 128-column groups), rows are strided over the remaining warps.
-template <bool kVec>
-__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, int nbits, int splits,
-                                                        uint32_t* __restrict__ out) {
+template <int NB, bool kVec>
+__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, uint32_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int gdy = s128(W);
     const int rows = p8(H);
-    const size_t wpr = (size_t)gdy * 4, plane = (size_t)rows * wpr;
-    const float ub = (float)(1 << nbits);
-    const unsigned keep = (1u << nbits) - 1u;
-    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned part = warp_id % (unsigned)splits, row0 = warp_id / (unsigned)splits, row_step = nwarps / (unsigned)splits;
-    if (row_step == 0 || row0 >= row_step) return;   // leftover warps when nwarps is not a multiple of splits
-    const int per = (gdy + splits - 1) / splits;
-    const int cg_begin = (int)part * per, cg_end = min(gdy, cg_begin + per);
-    const int p_of_lane = lane & 7, w_of_lane = lane >> 3;
-
-    for (unsigned r = row0; r < (unsigned)rows; r += row_step) {
-        const bool row_ok = r < (unsigned)H;
-        const float* xrow = x + (size_t)r * W;
-        uint32_t* orow = out + (size_t)r * wpr;
-        for (int cg0 = cg_begin; cg0 < cg_end; cg0 += kPackUnroll) {
-            float4 v[kPackUnroll];
+    const int wpr = s128(W) * 4;                       // words per output row
+    const int groups = (wpr + 31) >> 5;                // 32-word groups per row
+    const size_t plane = (size_t)rows * wpr;
+    const float ub = (float)(1 << NB);
+    const uint32_t keep4 = ((1u << NB) - 1u) * 0x01010101u;
+    const long long units = (long long)rows * groups;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = warp_id; u < units; u += nwarps) {
+        const int r = (int)(u / groups), g = (int)(u - (long long)r * groups);
+        const int wi = g * 32 + lane;
+        if (wi >= wpr) continue;
+        const int col0 = wi * 32;
+        uint32_t t[8];
 #pragma unroll
-            for (int j = 0; j < kPackUnroll; ++j) {
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int c = (cg0 + j) * 128 + 4 * lane;
-                if (row_ok && cg0 + j < cg_end && c < W) {
-                    const float* src = xrow + c;
-                    if (kVec) {
-                        v[j] = __ldcs(reinterpret_cast<const float4*>(src));  // streamed once
-                    } else {
-                        v[j].x = __ldcs(src);
-                        if (c + 1 < W) v[j].y = __ldcs(src + 1);
-                        if (c + 2 < W) v[j].z = __ldcs(src + 2);
-                        if (c + 3 < W) v[j].w = __ldcs(src + 3);
-                    }
-                }
-            }
+        for (int k = 0; k < 8; ++k) t[k] = 0u;
+        if (r < H && col0 < W) {
+            const float* src = x + (size_t)r * W + col0;
+            if (kVec && col0 + 32 <= W) {
+                float4 v[8];
 #pragma unroll
-            for (int j = 0; j < kPackUnroll; ++j) {
-                if (cg0 + j >= cg_end) break;  // warp-uniform
-                const unsigned q0 = (unsigned)quantize_val(v[j].x, ub) & keep;
-                const unsigned q1 = (unsigned)quantize_val(v[j].y, ub) & keep;
-                const unsigned q2 = (unsigned)quantize_val(v[j].z, ub) & keep;
-                const unsigned q3 = (unsigned)quantize_val(v[j].w, ub) & keep;
-                const unsigned t = (q0 << 24) | (q1 << 16) | (q2 << 8) | q3;
-                unsigned mine = 0;
-                for (int p = 0; p < nbits; ++p) {
-                    // bit p of the four values -> nibble, first column in the nibble's MSB
-                    const unsigned nib = (((t >> p) & 0x01010101u) * 0x01020408u) >> 24;
-                    unsigned w = nib << (28 - 4 * p_of_lane);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-                    if (p_of_lane == p) mine = w;
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(src) + k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t a0 = quantize_bits(v[k].x, ub), a1 = quantize_bits(v[k].y, ub);
+                    const uint32_t a2 = quantize_bits(v[k].z, ub), a3 = quantize_bits(v[k].w, ub);
+                    // low bytes of a0..a3, first element in the top byte
+                    t[k] = __byte_perm(__byte_perm(a3, a2, 0x0040u), __byte_perm(a1, a0, 0x0040u), 0x5410u) & keep4;
                 }
-                if (p_of_lane < nbits) orow[(size_t)p_of_lane * plane + (size_t)(cg0 + j) * 4 + w_of_lane] = mine;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t a[4] = {0x4B400000u, 0x4B400000u, 0x4B400000u, 0x4B400000u};   // quantize_bits(0)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (col0 + 4 * k + i < W) a[i] = quantize_bits(__ldg(src + 4 * k + i), ub);
+                    t[k] = __byte_perm(__byte_perm(a[3], a[2], 0x0040u), __byte_perm(a[1], a[0], 0x0040u), 0x5410u) & keep4;
+                }
             }
         }
+        uint32_t w[NB];
+        planes_from_bytes<NB>(t, w);
+        uint32_t* dst = out + (size_t)r * wpr + wi;
+#pragma unroll
+        for (int p = 0; p < NB; ++p) dst[(size_t)p * plane] = w[p];
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // COL layouts: word [p][c][kw] holds rows 32kw..32kw+31 of column c, MSB-first (a transposing
 // pack).  One warp handles a 32-row x 32-column tile: every row read is a coalesced 128-byte
-// request (all 32 in flight), each lane accumulates the word of its own column per plane.
+// request (all 32 in flight), each lane collects the 32 quantized values of its own column (four per
+// register) and extracts the plane words like the row kernel.
 // ------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(256) pack_col_kernel(const float* __restrict__ x, int H, int W, int col_limit,
@@ -95,7 +83,7 @@ __global__ void __launch_bounds__(256) pack_col_kernel(const float* __restrict__
     const unsigned units = (unsigned)kwords * (unsigned)cgroups;
     const size_t plane = (size_t)gdk * p128(W) * 4;   // reference kernel.h:88: always the P128 stride
     const float ub = (float)(1 << NB);
-    const unsigned keep = (1u << NB) - 1u;
+    const uint32_t keep4 = ((1u << NB) - 1u) * 0x01010101u;
     const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
 
@@ -107,15 +95,15 @@ __global__ void __launch_bounds__(256) pack_col_kernel(const float* __restrict__
             const int r = kw * 32 + i;
             v[i] = (r < H && c < W) ? __ldg(x + (size_t)r * W + c) : 0.f;
         }
-        uint32_t w[NB];
+        uint32_t t[8];
 #pragma unroll
-        for (int p = 0; p < NB; ++p) w[p] = 0u;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const unsigned q = (unsigned)quantize_val(v[i], ub) & keep;
-#pragma unroll
-            for (int p = 0; p < NB; ++p) w[p] |= ((q >> p) & 1u) << (31 - i);
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t a0 = quantize_bits(v[4 * k], ub), a1 = quantize_bits(v[4 * k + 1], ub);
+            const uint32_t a2 = quantize_bits(v[4 * k + 2], ub), a3 = quantize_bits(v[4 * k + 3], ub);
+            t[k] = __byte_perm(__byte_perm(a3, a2, 0x0040u), __byte_perm(a1, a0, 0x0040u), 0x5410u) & keep4;
         }
+        uint32_t w[NB];
+        planes_from_bytes<NB>(t, w);
         if (c < col_limit) {
 #pragma unroll
             for (int p = 0; p < NB; ++p) {
@@ -228,22 +216,21 @@ static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
 
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st) {
     if (layout == QGTC_LAYOUT_ROW) {
-        const int rows = p8(H), gdy = s128(W);
-        const long long units = (long long)rows * gdy;
-        const long long blocks = (units + 8 * kPackUnroll - 1) / (8 * kPackUnroll);
-        const int grid = grid_for(blocks, 8);
-        // warps sharing a row: only when there are fewer rows than warps
-        const long long nwarps = (long long)grid * 8;
-        int splits = 1;
-        if (rows < nwarps) {
-            splits = (int)(nwarps / rows);
-            const int max_splits = (gdy + kPackUnroll - 1) / kPackUnroll;
-            if (splits > max_splits) splits = max_splits;
-            if (splits < 1) splits = 1;
-        }
+        const int rows = p8(H), wpr = s128(W) * 4;
+        const long long units = (long long)rows * ((wpr + 31) / 32);     // warp-level units: (row, 32 output words)
+        const int grid = grid_for((units + 7) / 8, 8);
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
-        if (vec) pack_row_kernel<true><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
-        else pack_row_kernel<false><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
+#define QGTC_PACK_ROW(NB)                                                                    \
+    case NB:                                                                                  \
+        if (vec) pack_row_kernel<NB, true><<<grid, 256, 0, st>>>(in, H, W, out);              \
+        else pack_row_kernel<NB, false><<<grid, 256, 0, st>>>(in, H, W, out);                 \
+        break;
+        switch (nbits) {
+            QGTC_PACK_ROW(1) QGTC_PACK_ROW(2) QGTC_PACK_ROW(3) QGTC_PACK_ROW(4)
+            QGTC_PACK_ROW(5) QGTC_PACK_ROW(6) QGTC_PACK_ROW(7) QGTC_PACK_ROW(8)
+            default: return QGTC_ERR_UNSUPPORTED;
+        }
+#undef QGTC_PACK_ROW
         note_launch();
         return check_launch("pack_row_kernel");
     }

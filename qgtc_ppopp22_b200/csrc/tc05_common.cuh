@@ -228,20 +228,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f4(int n) {
 }
 
 
-// 8 x 8 bit-matrix transpose (Hacker's Delight 7-3) of eight bytes: x = rows 0..3 (row 0 in the top byte),
-// y = rows 4..7.  Afterwards byte (p - 4) of x (p >= 4) / byte p of y (p < 4), counted from the low end, holds
-// bit p of the eight rows with row 0 in its MSB -- the MSB-first order of the packed plane words.
-__device__ __forceinline__ void transpose8x8(uint32_t& x, uint32_t& y) {
-    uint32_t t;
-    t = (x ^ (x >> 7)) & 0x00AA00AAu;  x = x ^ t ^ (t << 7);
-    t = (y ^ (y >> 7)) & 0x00AA00AAu;  y = y ^ t ^ (t << 7);
-    t = (x ^ (x >> 14)) & 0x0000CCCCu; x = x ^ t ^ (t << 14);
-    t = (y ^ (y >> 14)) & 0x0000CCCCu; y = y ^ t ^ (t << 14);
-    t = (x & 0xF0F0F0F0u) | ((y >> 4) & 0x0F0F0F0Fu);
-    y = ((x << 4) & 0xF0F0F0F0u) | (y & 0x0F0F0F0Fu);
-    x = t;
-}
-
+// transpose8x8 (8 x 8 bit-matrix transpose) lives in common.cuh: the pack kernels use it too
 // Requantize of QGTC_layer_hidden (reference kernel.h:31-37) followed by the "keep bits 0..ob-1" of the packing.
 // NN: the accumulator is known to be non-negative (scaled expansion modes: no int32 wrap possible).
 template <bool NN>

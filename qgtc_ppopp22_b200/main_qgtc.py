@@ -50,6 +50,7 @@ def build_parser():
     p.add_argument("--tile-bitmap", choices=["auto", "on", "off"], default="auto",
                    help="--grouped: pass the batches' tile bitmaps (zero-tile jumping); auto = when under half of the tiles are non-zero")
     p.add_argument("--min-region-ms", type=float, default=0.0, help="--cuda-graph: replay enough epochs for a timed region of at least this many ms")
+    p.add_argument("--gather-logits", action="store_true", help="after the timed epochs, all_gather every batch's logits to all ranks (NCCL)")
     p.add_argument("--dense-pack", action="store_true", help="build batches through the dense fp32 n x n adjacency as sampler.py:87-89 does "
                                                               "(default: packed straight from the edge list)")
     return p
@@ -255,6 +256,15 @@ def run(args, graph=None, quiet=False, ops=None):
               "batches": len(it), "world": world, "grouped": grouped,
               "tile_bitmaps_used": bool(grouped and gmaps), "nonzero_tile_fraction": it.nonzero_tile_fraction() if it.tile_maps else None,
               "checksum": float(last.sum().item()) if last is not None else 0.0, "nodes_per_batch": int(np.mean(counts))}
+    if getattr(args, "gather_logits", False):
+        # one more (untimed) forward that keeps every batch's logits, then the only data collective of the path
+        if grouped:
+            mine = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw)
+        else:
+            mine = [fwd(QGTC, c.bit_A, c.bit_X, W, p_[0], p_[3], bw) for c, p_ in it]
+        full = C.gather_logits(list(mine), list(it.batch_ids), counts, world)
+        result["logits_checksum_all_batches"] = float(sum(float(t.double().sum().item()) for t in full))
+        result["logits_batches_gathered"] = len(full)
     if args.cpu_baseline and rank == 0:
         from qgtc_ppopp22_b200 import dgl_baseline
         full = it if world == 1 else C.ClusterIter(args.dataset, graph, args.psize, args.batch_size, None, bit_width=bw,

@@ -82,7 +82,13 @@ def _rank_main(rank, world, port, q):
     dist.all_reduce(mine)                                                 # every batch owned by exactly one rank
     t = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                              # the epoch time is the slowest rank's
-    q.put((rank, mine.tolist(), float(t.item()), [int(c) for c in counts]))
+    # the logits gather (the path's only data collective): every rank ends up with every batch's logits, in batch order
+    logits = [torch.full((counts[b], 3), float(b)) + torch.arange(counts[b], dtype=torch.float32).view(-1, 1) for b in shards[rank]]
+    full = C.gather_logits(logits, shards[rank], counts, world)
+    ok = len(full) == len(counts) and all(
+        tuple(full[b].shape) == (counts[b], 3) and float(full[b][0, 0]) == float(b) and float(full[b][-1, 2]) == float(b + counts[b] - 1)
+        for b in range(len(counts)))
+    q.put((rank, mine.tolist(), float(t.item()), [int(c) for c in counts], ok))
     dist.destroy_process_group()
 
 
@@ -98,6 +104,7 @@ def test_two_rank_sharding_over_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, owned, tmax, counts in res:
+    for rank, owned, tmax, counts, gathered_ok in res:
         assert owned == [1] * len(counts)
         assert tmax == 11.0
+        assert gathered_ok

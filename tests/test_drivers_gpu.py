@@ -75,6 +75,10 @@ def test_epoch_runner_eager_and_graph():
     a.cuda_graph, a.grouped = True, True
     r7 = drv.run(a, graph=g, quiet=True)
     assert r6["checksum"] == r7["checksum"]
+    # the logits gather (single rank: concatenation in batch order)
+    a.gather_logits = True
+    r8 = drv.run(a, graph=g, quiet=True)
+    assert r8["logits_batches_gathered"] == 3 and r8["logits_checksum_all_batches"] != 0.0
 
 
 @pytest.mark.parametrize("run_gin", [False, True])
