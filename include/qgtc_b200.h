@@ -61,6 +61,11 @@ typedef enum qgtc_gemm_engine {
 #define QGTC_FLAG_NO_ZERO_JUMP 0x1u /* do not skip all-zero adjacency tiles (for A/B timing)        */
 #define QGTC_FLAG_COL_REF_QUIRK 0x2u /* bitmm2bit_col: reproduce the shipped kernel's stores exactly */
 #define QGTC_FLAG_TC05_PAIR 0x4u    /* tcgen05 engine: 2-CTA clusters, tcgen05.mma.cta_group::2 (M = 256)  */
+/* Grouped engine, programmatic dependent launch: the caller declares that an operand was NOT written by the work queued
+ * just before this call on the stream (adjacency and its tile bitmap, weights).  The kernel may then load it while the
+ * preceding kernel is still draining; operands without the flag are read only after that kernel has completed. */
+#define QGTC_FLAG_X1_STATIC 0x8u
+#define QGTC_FLAG_X2_STATIC 0x10u
 
 int qgtc_abi_version(void);
 const char* qgtc_strerror(int status);

@@ -16,7 +16,7 @@ from . import lib_dir
 
 ENGINE_AUTO, ENGINE_MMA_SYNC, ENGINE_TCGEN05, ENGINE_GROUPED = 0, 1, 2, 3
 GROUP_BITS_ROW, GROUP_FLOAT, GROUP_BITS_COL = 0, 1, 2
-FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK, FLAG_TC05_PAIR = 0x1, 0x2, 0x4
+FLAG_NO_ZERO_JUMP, FLAG_COL_REF_QUIRK, FLAG_TC05_PAIR, FLAG_X1_STATIC, FLAG_X2_STATIC = 0x1, 0x2, 0x4, 0x8, 0x10
 LAYOUT_ROW, LAYOUT_COL128, LAYOUT_COL8 = 0, 1, 2
 
 # every symbol include/qgtc_b200.h declares (checked by tests/test_abi.py)

@@ -68,7 +68,7 @@ static int check_device() {
 // flag bits a caller may set; the tcgen05 timing-experiment knobs (0x10000..0x400000, results are wrong by design)
 // are accepted only when QGTC_TC05_DEBUG_KNOBS=1 is set in the environment
 static bool flags_ok(unsigned flags) {
-    const unsigned documented = QGTC_FLAG_NO_ZERO_JUMP | QGTC_FLAG_COL_REF_QUIRK | QGTC_FLAG_TC05_PAIR;
+    const unsigned documented = QGTC_FLAG_NO_ZERO_JUMP | QGTC_FLAG_COL_REF_QUIRK | QGTC_FLAG_TC05_PAIR | QGTC_FLAG_X1_STATIC | QGTC_FLAG_X2_STATIC;
     if ((flags & ~documented) == 0) return true;
     static const bool knobs = [] { const char* e = std::getenv("QGTC_TC05_DEBUG_KNOBS"); return e && e[0] == '1'; }();
     return knobs && (flags & ~(documented | 0x6F0000u)) == 0;

@@ -71,7 +71,7 @@ struct GrpArgs {
     int count, units;
     int N, NP, bit1, bit2, out_bit, epi, pad128;
     int cps, stages, dbufs, groups;           // chunks per item, A/B ring depth, accumulator buffers, expander groups in use
-    int a_slot_bytes, b_slot_bytes, b_stage_bytes, b_ring, max_nst, mode2;
+    int a_slot_bytes, b_slot_bytes, b_stage_bytes, b_ring, max_nst, mode2, any_bitmap;
     int off_bstage, off_bring, off_bars, off_flags, off_misc, off_units;   // shared-memory offsets from the 1024-byte aligned base
     unsigned int cps_inv;
     unsigned flags;
@@ -247,12 +247,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     }
     if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 512);
 
-    // ---- work lists (kernel parameters only: nothing here depends on the previous kernel, so it runs before the wait below)
+    if (T.any_bitmap && !(T.flags & QGTC_FLAG_X1_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // the lists read the tile bitmaps
+    // ---- work lists (kernel parameters, and tile bitmaps: nothing here depends on the previous kernel)
     const int units_here = (T.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int units_cap = (T.units + (int)gridDim.x - 1) / (int)gridDim.x;       // the launcher sized the lists for this many units per CTA
     ItemRec* items = reinterpret_cast<ItemRec*>(smem + T.off_units + units_cap * (int)sizeof(UnitRec));
     unsigned char* reuse_flag = reinterpret_cast<unsigned char*>(items + units_cap * T.max_nst);
-    for (int k = threadIdx.x; k < units_here; k += kThreads) {
+    // One warp per unit: the problem index is a warp-uniform constant-bank read, the 64-byte descriptor one read per lane
+    // from a single line (per-thread searches through the parameter table serialise in the constant cache).
+    for (int k = warp; k < units_here; k += kThreads / 32) {
         const int u = (int)blockIdx.x + k * (int)gridDim.x;
         int z;
         if (T.units <= kUnitTable) {
@@ -265,19 +268,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             }
             z = lo;
         }
-        const GrpProblem& P = T.p[z];
-        UnitRec r;
-        r.x1 = P.x1; r.x2 = P.x2; r.out = P.out;
-        r.x1_words = P.x1_words; r.x2_words = P.x2_words;
-        r.M = P.M;
-        r.gdk = s128(P.K);
-        r.mt = u - P.unit0;
-        r.bm = P.bitmap ? P.bitmap + (size_t)r.mt * ((r.gdk + 31) >> 5) : nullptr;
-        r.item0 = r.bm ? walk_bitmap_stages(r.bm, r.gdk, CPS, T.cps_inv, [](int) {}) : (r.gdk + CPS - 1) / CPS;   // count, for now
-        units[k] = r;
+        uint32_t* raw = reinterpret_cast<uint32_t*>(&units[k]);
+        if (lane < 16) raw[lane] = reinterpret_cast<const uint32_t*>(&T.p[z])[lane];
+        __syncwarp();
+        if (lane == 0) {
+            const GrpProblem P = *reinterpret_cast<const GrpProblem*>(raw);
+            UnitRec r;
+            r.x1 = P.x1; r.x2 = P.x2; r.out = P.out;
+            r.x1_words = P.x1_words; r.x2_words = P.x2_words;
+            r.M = P.M;
+            r.gdk = s128(P.K);
+            r.mt = u - P.unit0;
+            r.bm = P.bitmap ? P.bitmap + (size_t)r.mt * ((r.gdk + 31) >> 5) : nullptr;
+            r.item0 = r.bm ? walk_bitmap_stages(r.bm, r.gdk, CPS, T.cps_inv, [](int) {}) : (r.gdk + CPS - 1) / CPS;   // count, for now
+            units[k] = r;
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {        // exclusive scan of the per-unit item counts (one warp; a CTA has at most a few hundred units)
+    if (warp == 0) {       // item lists: an exclusive scan of the per-unit item counts, then lane k writes the items of unit base + k
         int carry = 0;
         for (int base = 0; base < units_here; base += 32) {
             const int k = base + lane;
@@ -288,28 +296,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            if (k < units_here) units[k].item0 = carry + incl - c;
+            if (k < units_here) {
+                const UnitRec& r = units[k];
+                const int first = carry + incl - c, gdk = r.gdk;
+                int i = first;
+                auto put = [&](int st) {
+                    ItemRec it;
+                    it.c0 = st * CPS;
+                    it.unit = (unsigned short)k;
+                    it.nch = (unsigned char)(gdk - it.c0 < CPS ? gdk - it.c0 : CPS);
+                    it.flags = (unsigned char)(i == first ? 1 : 0);
+                    items[i++] = it;
+                };
+                if (r.bm) walk_bitmap_stages(r.bm, gdk, CPS, T.cps_inv, put);
+                else for (int st = 0; st * CPS < gdk; ++st) put(st);
+                items[i - 1].flags |= 2;
+                units[k].item0 = first;
+            }
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) *n_items_slot = carry;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < units_here; k += kThreads) {
-        const UnitRec& r = units[k];
-        int i = r.item0;
-        const int gdk = r.gdk;
-        auto put = [&](int st) {
-            ItemRec it;
-            it.c0 = st * CPS;
-            it.unit = (unsigned short)k;
-            it.nch = (unsigned char)(gdk - it.c0 < CPS ? gdk - it.c0 : CPS);
-            it.flags = 0;
-            items[i++] = it;
-        };
-        if (r.bm) walk_bitmap_stages(r.bm, gdk, CPS, T.cps_inv, put);
-        else for (int st = 0; st * CPS < gdk; ++st) put(st);
-        items[r.item0].flags |= 1;
-        items[i - 1].flags |= 2;
     }
     tc_fence_before();
     __syncthreads();
@@ -317,9 +323,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     const int n_items = *n_items_slot;
     if (threadIdx.x == 32) QGTC_GTRACE(7, 2);
-    // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results (this kernel's
-    // operands) are complete and visible only after this wait.  No-op for a normal launch.
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    // Programmatic dependent launch: this grid may start while the previous kernel of the stream is still running (its CTAs
+    // take over SMs as that kernel's CTAs retire).  Memory the previous kernel writes -- or still reads -- may only be touched
+    // after griddepcontrol.wait (no-op for a normal launch).  Each role waits where it first needs it: the epilogue before
+    // its first store, expanders / converters before their first load unless the caller declared that operand static
+    // (QGTC_FLAG_X1_STATIC / QGTC_FLAG_X2_STATIC: adjacency, weights), so those loads overlap the previous kernel's tail.
     if (threadIdx.x == 32) QGTC_GTRACE(7, 3);
 
     const int dcols = T.dbufs * NP;                // accumulators first, then the A stages
@@ -339,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             unsigned char* ring = a_rings + (size_t)warp * kARing * T.a_slot_bytes + lane * 16;   // piece i of this lane at + i * 512
             const int trole = warp == 0 ? 0 : (warp == 4 ? 1 : -1);
             const bool tr = TRACE && trole >= 0 && tlane;
+            if (!(T.flags & QGTC_FLAG_X1_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");
             if (tr) QGTC_GTRACE(trole, 10);
             int s = g % S;                         // stage and use count of the item being consumed
             uint32_t use = (uint32_t)(g / S);
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             reuse_flag[it] = same ? 1 : 0;
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(kConvThreads) : "memory");     // the four converter warps only
+        if (!(T.flags & QGTC_FLAG_X2_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");
         unsigned char* ring = b_ring + t * 16;                         // piece (i, plane) of this thread at + (i * bit2 + plane) * 2048
         const bool tr = TRACE && warp == kConvWarp0 && tlane;
         if (tr) QGTC_GTRACE(2, 20);
@@ -577,6 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const int N = T.N, ob = T.out_bit;
         int buf = 0;
         uint32_t duse = 0;
+        asm volatile("griddepcontrol.wait;\n" ::: "memory");       // the output may alias memory the previous kernel still reads
 #pragma unroll 1
         for (int tl = 0; tl < units_here; ++tl) {
             const UnitRec& P = units[tl];
@@ -758,7 +769,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
     while (first < count) {
         // as many problems as the parameter table and the per-CTA work lists hold
         long long units = 0;
-        int n = 0, max_nst = 1, max_gdk = 1;
+        int n = 0, max_nst = 1, max_gdk = 1, any_bitmap = 0;
         while (first + n < count && n < limit) {
             const GroupedProblemHost& h = probs[first + n];
             const long long u = (p8(h.M) + 127) / 128;
@@ -766,6 +777,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             GrpProblem& p = T.p[n];
             p.x1 = h.x1; p.x2 = h.x2; p.out = h.out;
             p.bitmap = bit1 == 1 ? h.bitmap : nullptr;
+            if (p.bitmap) any_bitmap = 1;
             p.x1_words = h.x1_words; p.x2_words = h.x2_words;
             p.M = h.M; p.K = h.K;
             p.unit0 = (int)units;
@@ -804,6 +816,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         const int units_per_cta = (T.units + grid - 1) / grid;
         const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * ((int)sizeof(ItemRec) + 1);
         T.max_nst = max_nst;
+        T.any_bitmap = any_bitmap;
         {   // expansion mode 2 (1-bit A only): the 8 x scaled sums must fit an int32 and the scaled features a byte
             static const bool no_mode2 = [] { const char* e = getenv("QGTC_GRP_MODE2"); return e && e[0] == '0'; }();
             const double max_sum = (double)max_gdk * 128.0 * (double)((1u << bit2) - 1u);

@@ -4,9 +4,82 @@
 // and UnPackFc* (kernel.h:109-201).  One fused pass: fp32 is read once with 128-bit loads, the
 // int32 temporary of the reference (QGTC_device.cu:63) does not exist, every output word is
 // written (no pre-zeroed output needed).  HBM-bound: 4 B/element read, nbits/8 B/element written.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace qgtc {
+
+// ------------------------------------------------------------------------------------------
+// ROW layout, shuffle variant (small or oddly aligned inputs, one or two planes): a warp handles (row, 128-column group)
+// units: lane l owns columns 4l..4l+3 (one float4, or four scalars when the row is not 16-byte aligned), turns them into
+// one nibble per plane, and an 8-lane OR-butterfly assembles the four words.  Finer work units than the word-per-lane
+// kernel below (more parallelism for small matrices) and coalesced for any alignment.
+// ------------------------------------------------------------------------------------------
+constexpr int kPackUnroll = 4;
+
+// Work decomposition without divisions in the loop: `splits` warps share a row (each takes a contiguous
+// range of 128-column groups), rows are strided over the remaining warps.
+template <bool kVec>
+__global__ void __launch_bounds__(256) pack_row_shfl_kernel(const float* __restrict__ x, int H, int W, int nbits, int splits,
+                                                             uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int gdy = s128(W);
+    const int rows = p8(H);
+    const size_t wpr = (size_t)gdy * 4, plane = (size_t)rows * wpr;
+    const float ub = (float)(1 << nbits);
+    const uint32_t keep4 = ((1u << nbits) - 1u) * 0x01010101u;
+    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned part = warp_id % (unsigned)splits, row0 = warp_id / (unsigned)splits, row_step = nwarps / (unsigned)splits;
+    if (row_step == 0 || row0 >= row_step) return;   // leftover warps when nwarps is not a multiple of splits
+    const int per = (gdy + splits - 1) / splits;
+    const int cg_begin = (int)part * per, cg_end = min(gdy, cg_begin + per);
+    const int p_of_lane = lane & 7, w_of_lane = lane >> 3;
+
+    for (unsigned r = row0; r < (unsigned)rows; r += row_step) {
+        const bool row_ok = r < (unsigned)H;
+        const float* xrow = x + (size_t)r * W;
+        uint32_t* orow = out + (size_t)r * wpr;
+        for (int cg0 = cg_begin; cg0 < cg_end; cg0 += kPackUnroll) {
+            float4 v[kPackUnroll];
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c = (cg0 + j) * 128 + 4 * lane;
+                if (row_ok && cg0 + j < cg_end && c < W) {
+                    const float* src = xrow + c;
+                    if (kVec) {
+                        v[j] = __ldcs(reinterpret_cast<const float4*>(src));  // streamed once
+                    } else {
+                        v[j].x = __ldcs(src);
+                        if (c + 1 < W) v[j].y = __ldcs(src + 1);
+                        if (c + 2 < W) v[j].z = __ldcs(src + 2);
+                        if (c + 3 < W) v[j].w = __ldcs(src + 3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; ++j) {
+                if (cg0 + j >= cg_end) break;  // warp-uniform
+                const uint32_t a0 = quantize_bits(v[j].x, ub), a1 = quantize_bits(v[j].y, ub);
+                const uint32_t a2 = quantize_bits(v[j].z, ub), a3 = quantize_bits(v[j].w, ub);
+                const uint32_t t = __byte_perm(__byte_perm(a3, a2, 0x0040u), __byte_perm(a1, a0, 0x0040u), 0x5410u) & keep4;
+                unsigned mine = 0;
+                for (int p = 0; p < nbits; ++p) {
+                    // bit p of the four values -> nibble, first column in the nibble's MSB
+                    const unsigned nib = (((t >> p) & 0x01010101u) * 0x01020408u) >> 24;
+                    unsigned w = nib << (28 - 4 * p_of_lane);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                    if (p_of_lane == p) mine = w;
+                }
+                if (p_of_lane < nbits) orow[(size_t)p_of_lane * plane + (size_t)(cg0 + j) * 4 + w_of_lane] = mine;
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // ROW layout: word [p][r][w] holds columns 32w..32w+31 of row r, MSB-first.
@@ -40,7 +113,10 @@ __global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__
             if (kVec && col0 + 32 <= W) {
                 float4 v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(src) + k);
+                for (int k = 0; k < 8; ++k)     // volatile asm: all eight 16-byte loads of the line are issued before the first use
+                    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                                 : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w)
+                                 : "l"(reinterpret_cast<const float4*>(src) + k));
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t a0 = quantize_bits(v[k].x, ub), a1 = quantize_bits(v[k].y, ub);
@@ -216,23 +292,45 @@ static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
 
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st) {
     if (layout == QGTC_LAYOUT_ROW) {
-        const int rows = p8(H), wpr = s128(W) * 4;
-        const long long units = (long long)rows * ((wpr + 31) / 32);     // warp-level units: (row, 32 output words)
-        const int grid = grid_for((units + 7) / 8, 8);
+        const int rows = p8(H), wpr = s128(W) * 4, gdy = s128(W);
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
-#define QGTC_PACK_ROW(NB)                                                                    \
-    case NB:                                                                                  \
-        if (vec) pack_row_kernel<NB, true><<<grid, 256, 0, st>>>(in, H, W, out);              \
-        else pack_row_kernel<NB, false><<<grid, 256, 0, st>>>(in, H, W, out);                 \
-        break;
-        switch (nbits) {
-            QGTC_PACK_ROW(1) QGTC_PACK_ROW(2) QGTC_PACK_ROW(3) QGTC_PACK_ROW(4)
-            QGTC_PACK_ROW(5) QGTC_PACK_ROW(6) QGTC_PACK_ROW(7) QGTC_PACK_ROW(8)
-            default: return QGTC_ERR_UNSUPPORTED;
-        }
+        // Two kernels, chosen by measurement (profiles/r2_pack_bench_*.txt): the word-per-lane kernel (no shuffles, bit
+        // transposes) wins on large 16-byte-aligned inputs from three planes up; the shuffle kernel has finer work units
+        // (small matrices), is coalesced for any alignment, and is ahead at one or two planes.  QGTC_PACK_ROW=word|shfl forces one.
+        static const int force = [] { const char* e = getenv("QGTC_PACK_ROW"); return !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 's' ? 2 : 0)); }();
+        const long long word_units = (long long)rows * ((wpr + 31) / 32);     // warp-level units of the word kernel: (row, 32 output words)
+        bool use_word = vec && nbits >= 3 && W >= 1024 && word_units >= 2ll * kNumSMs * 8;
+        if (force == 1) use_word = vec;
+        if (force == 2) use_word = false;
+        if (use_word) {
+            const int grid = grid_for((word_units + 7) / 8, 8);
+#define QGTC_PACK_ROW(NB) \
+    case NB: pack_row_kernel<NB, true><<<grid, 256, 0, st>>>(in, H, W, out); break;
+            switch (nbits) {
+                QGTC_PACK_ROW(1) QGTC_PACK_ROW(2) QGTC_PACK_ROW(3) QGTC_PACK_ROW(4)
+                QGTC_PACK_ROW(5) QGTC_PACK_ROW(6) QGTC_PACK_ROW(7) QGTC_PACK_ROW(8)
+                default: return QGTC_ERR_UNSUPPORTED;
+            }
 #undef QGTC_PACK_ROW
+            note_launch();
+            return check_launch("pack_row_kernel");
+        }
+        const long long units = (long long)rows * gdy;
+        const long long blocks = (units + 8 * kPackUnroll - 1) / (8 * kPackUnroll);
+        const int grid = grid_for(blocks, 8);
+        // warps sharing a row: only when there are fewer rows than warps
+        const long long nwarps = (long long)grid * 8;
+        int splits = 1;
+        if (rows < nwarps) {
+            splits = (int)(nwarps / rows);
+            const int max_splits = (gdy + kPackUnroll - 1) / kPackUnroll;
+            if (splits > max_splits) splits = max_splits;
+            if (splits < 1) splits = 1;
+        }
+        if (vec) pack_row_shfl_kernel<true><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
+        else pack_row_shfl_kernel<false><<<grid, 256, 0, st>>>(in, H, W, nbits, splits, out);
         note_launch();
-        return check_launch("pack_row_kernel");
+        return check_launch("pack_row_shfl_kernel");
     }
     const int col_limit = layout == QGTC_LAYOUT_COL128 ? p128(W) : p8(W);
     if (layout == QGTC_LAYOUT_COL8 && nbits > 1 && p8(W) != p128(W)) {

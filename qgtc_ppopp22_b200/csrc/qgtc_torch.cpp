@@ -220,13 +220,16 @@ torch::Tensor bitMM2Int(torch::Tensor bit_X1, torch::Tensor bit_X2, const int X1
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// static_operands (grouped ops): bit 0 = every X1 (and its tile bitmap), bit 1 = every X2 was NOT produced by the work queued
+// just before this call (adjacency, weights): QGTC_FLAG_X1_STATIC / QGTC_FLAG_X2_STATIC, see include/qgtc_b200.h.
 // Extensions beyond the reference's eight functions (keyword arguments allowed here): the grouped launch -- one op of the
 // forward for ALL batches in one kernel (include/qgtc_b200.h: qgtc_bitmm_grouped) -- the tile bitmap for zero-tile jumping
 // and batch construction from an edge list.
 // ---------------------------------------------------------------------------------------------------------------------
 std::vector<torch::Tensor> grouped_impl(const std::vector<torch::Tensor>& X1s, const std::vector<torch::Tensor>& X2s,
                                         const std::vector<int64_t>& Ms, const std::vector<int64_t>& Ks, int N, int bit1, int bit2,
-                                        int out_bit, int kind, bool pad_128, const std::vector<torch::Tensor>& tile_maps, const char* op) {
+                                        int out_bit, int kind, bool pad_128, const std::vector<torch::Tensor>& tile_maps, unsigned static_flags,
+                                        const char* op) {
     const size_t count = X1s.size();
     TORCH_CHECK(count > 0 && X2s.size() == count && Ms.size() == count && Ks.size() == count, op, ": operand lists must be non-empty and of equal length");
     TORCH_CHECK(tile_maps.empty() || tile_maps.size() == count, op, ": tile_maps must be empty or hold one bitmap per problem");
@@ -270,22 +273,24 @@ std::vector<torch::Tensor> grouped_impl(const std::vector<torch::Tensor>& X1s, c
         p.M = (int32_t)Ms[i];
         p.K = (int32_t)Ks[i];
     }
-    check_status(qgtc_bitmm_grouped(probs.data(), (int)count, N, bit1, bit2, out_bit, kind, pad_128 ? 1 : 0, engine_from_env(), flags_from_env(),
-                                    current_stream()), op);
+    check_status(qgtc_bitmm_grouped(probs.data(), (int)count, N, bit1, bit2, out_bit, kind, pad_128 ? 1 : 0, engine_from_env(),
+                                    flags_from_env() | (static_flags & (QGTC_FLAG_X1_STATIC | QGTC_FLAG_X2_STATIC)), current_stream()), op);
     return outs;
 }
 
 std::vector<torch::Tensor> bitMM2Bit_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
-                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, int out_bit, std::vector<torch::Tensor> tile_maps) {
-    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_ROW, true, tile_maps, "bitMM2Bit_grouped");
+                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, int out_bit, std::vector<torch::Tensor> tile_maps,
+                                             int static_operands) {
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_ROW, true, tile_maps, (unsigned)static_operands << 3, "bitMM2Bit_grouped");
 }
 std::vector<torch::Tensor> bitMM2Bit_col_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
                                                  std::vector<int64_t> Ks, int N, int bit1, int bit2, int out_bit) {
-    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_COL, true, {}, "bitMM2Bit_col_grouped");
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_COL, true, {}, 0u, "bitMM2Bit_col_grouped");
 }
 std::vector<torch::Tensor> bitMM2Int_grouped(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms,
-                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, bool pad_128, std::vector<torch::Tensor> tile_maps) {
-    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, 1, QGTC_GROUP_FLOAT, pad_128, tile_maps, "bitMM2Int_grouped");
+                                             std::vector<int64_t> Ks, int N, int bit1, int bit2, bool pad_128, std::vector<torch::Tensor> tile_maps,
+                                             int static_operands) {
+    return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, 1, QGTC_GROUP_FLOAT, pad_128, tile_maps, (unsigned)static_operands << 3, "bitMM2Int_grouped");
 }
 
 torch::Tensor tile_bitmap(torch::Tensor bit_X1, const int M, const int K) {
@@ -330,12 +335,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     namespace py = pybind11;
     m.def("bitMM2Bit_grouped", &bitMM2Bit_grouped, "one launch: bitMM2Bit of every problem of a list (same N and bit widths)", py::arg("X1s"),
           py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"),
-          py::arg("tile_maps") = std::vector<torch::Tensor>());
+          py::arg("tile_maps") = std::vector<torch::Tensor>(), py::arg("static_operands") = 0);
     m.def("bitMM2Bit_col_grouped", &bitMM2Bit_col_grouped, "one launch: bitMM2Bit_col (column-major output) of every problem of a list", py::arg("X1s"),
           py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"));
     m.def("bitMM2Int_grouped", &bitMM2Int_grouped, "one launch: bitMM2Int of every problem of a list (same N and bit widths)", py::arg("X1s"),
           py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("pad_128"),
-          py::arg("tile_maps") = std::vector<torch::Tensor>());
+          py::arg("tile_maps") = std::vector<torch::Tensor>(), py::arg("static_operands") = 0);
     m.def("tile_bitmap", &tile_bitmap, "non-zero 128 x 128-bit tile bitmap of a packed 1-bit adjacency (zero-tile jumping)");
     m.def("edges2bit", &edges2bit, "packed 1-bit adjacency R(1,H,W) from int32 edge endpoints (no dense fp32 intermediate)");
     m.attr("__backend__") = "qgtc_b200";

@@ -57,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     uint32_t spins = 0;
     if (hinted) {   // a failed hinted try_wait sleeps on the barrier (NANOSLEEP.SYNCS), so the bound is generous in time
         while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
-            if (++spins > (1u << 13)) {   // ~8 s of 1 ms suspensions: only a protocol deadlock gets here
+            if (++spins > (1u << 16)) {   // ~65 s of 1 ms suspensions (a sanitizer run is orders of magnitude slower than normal): only a protocol deadlock gets here
                 if (error_flag) { atomicExch_system(error_flag, 0x80000000u | (unsigned)where); __threadfence_system(); }
                 __trap();
             }

@@ -86,19 +86,22 @@ def grouped_forward(QGTC, run_gin, A, X, tile_maps, W, ns, D, bw):
     bit_W1, bit_W2, bit_W3, h1, h2, out = W
     B = len(A)
     W1, W2, W3 = [bit_W1] * B, [bit_W2] * B, [bit_W3] * B
+    # static_operands: the adjacency (X1 of the aggregations, with its tile bitmap) and the weights (X2 of the updates) are not
+    # produced by the previous op, so the kernel may load them while that op is still draining (programmatic dependent launch)
+    SA, SW = 1, 2
     if run_gin:
-        o = QGTC.bitMM2Bit_grouped(A, X, ns, ns, D, 1, bw, bw, tile_maps)
-        o = QGTC.bitMM2Bit_grouped(o, W1, ns, [D] * B, h1, bw, bw, bw)
-        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps)
-        o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw)
-        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps)
-        return QGTC.bitMM2Int_grouped(o, W3, ns, [h2] * B, out, bw, bw, False)
-    o = QGTC.bitMM2Bit_grouped(X, W1, ns, [D] * B, h1, bw, bw, bw)
-    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps)
-    o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw)
-    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps)
-    o = QGTC.bitMM2Bit_grouped(o, W3, ns, [h2] * B, out, bw, bw, bw)
-    return QGTC.bitMM2Int_grouped(A, o, ns, ns, h2, 1, bw, False, tile_maps)
+        o = QGTC.bitMM2Bit_grouped(A, X, ns, ns, D, 1, bw, bw, tile_maps, SA | SW)
+        o = QGTC.bitMM2Bit_grouped(o, W1, ns, [D] * B, h1, bw, bw, bw, [], SW)
+        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps, SA)
+        o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw, [], SW)
+        o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps, SA)
+        return QGTC.bitMM2Int_grouped(o, W3, ns, [h2] * B, out, bw, bw, False, [], SW)
+    o = QGTC.bitMM2Bit_grouped(X, W1, ns, [D] * B, h1, bw, bw, bw, [], SA | SW)
+    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h1, 1, bw, bw, tile_maps, SA)
+    o = QGTC.bitMM2Bit_grouped(o, W2, ns, [h1] * B, h2, bw, bw, bw, [], SW)
+    o = QGTC.bitMM2Bit_grouped(A, o, ns, ns, h2, 1, bw, bw, tile_maps, SA)
+    o = QGTC.bitMM2Bit_grouped(o, W3, ns, [h2] * B, out, bw, bw, bw, [], SW)
+    return QGTC.bitMM2Int_grouped(A, o, ns, ns, h2, 1, bw, False, tile_maps, SA)
 
 
 def pack_weights(QGTC, feat_size, hidden, output, bw, device):

@@ -90,4 +90,4 @@ def test_undocumented_flag_bits_are_refused():
     L = capi.lib()
     # the tcgen05 timing knobs (0x10000..) produce wrong results by design: refused unless QGTC_TC05_DEBUG_KNOBS=1
     assert L.qgtc_bitmm2bit(16, 64, 16, 64, 8, 8, 8, 1, 1, 1, 16, 64, 0, 0x10000, None) == 1
-    assert L.qgtc_bitmm2bit(16, 64, 16, 64, 8, 8, 8, 1, 1, 1, 16, 64, 0, 0x8, None) == 1
+    assert L.qgtc_bitmm2bit(16, 64, 16, 64, 8, 8, 8, 1, 1, 1, 16, 64, 0, 0x20, None) == 1
