@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) pack_row_shfl_kernel(const float* __restr
 // (quantize_bits), the plane words come from multiply-gathers (up to 3 planes) or 8 x 8 bit transposes (4 planes and up).
 // ------------------------------------------------------------------------------------------
 template <int NB, bool kVec>
-__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__ x, int H, int W, uint32_t* __restrict__ out, int vec8) {
     const int lane = threadIdx.x & 31;
     const int rows = p8(H);
     const int wpr = s128(W) * 4;                       // words per output row
@@ -112,11 +112,20 @@ __global__ void __launch_bounds__(256) pack_row_kernel(const float* __restrict__
             const float* src = x + (size_t)r * W + col0;
             if (kVec && col0 + 32 <= W) {
                 float4 v[8];
+                if (vec8) {     // 32-byte aligned rows: four 256-bit loads, one whole sector each (LDG.E.256)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)     // volatile asm: all eight 16-byte loads of the line are issued before the first use
-                    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-                                 : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w)
-                                 : "l"(reinterpret_cast<const float4*>(src) + k));
+                    for (int k = 0; k < 4; ++k)
+                        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                                     : "=f"(v[2 * k].x), "=f"(v[2 * k].y), "=f"(v[2 * k].z), "=f"(v[2 * k].w), "=f"(v[2 * k + 1].x),
+                                       "=f"(v[2 * k + 1].y), "=f"(v[2 * k + 1].z), "=f"(v[2 * k + 1].w)
+                                     : "l"(src + 8 * k));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                                     : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w)
+                                     : "l"(reinterpret_cast<const float4*>(src) + k));
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t a0 = quantize_bits(v[k].x, ub), a1 = quantize_bits(v[k].y, ub);
@@ -294,18 +303,19 @@ int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_
     if (layout == QGTC_LAYOUT_ROW) {
         const int rows = p8(H), wpr = s128(W) * 4, gdy = s128(W);
         const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
-        // Two kernels, chosen by measurement (profiles/r2_pack_bench_*.txt): the word-per-lane kernel (no shuffles, bit
-        // transposes) wins on large 16-byte-aligned inputs from three planes up; the shuffle kernel has finer work units
-        // (small matrices), is coalesced for any alignment, and is ahead at one or two planes.  QGTC_PACK_ROW=word|shfl forces one.
+        // Two kernels, chosen by measurement (profiles/r2_pack_bench_*.txt): the word-per-lane kernel (256-bit loads, no shuffles,
+        // bit transposes) wins on large 16-byte-aligned inputs at every width (4096^2: 0.64-0.67 of HBM vs 0.38-0.59; 8192^2: 0.79-0.80);
+        // the shuffle kernel has finer work units (small matrices) and is coalesced for any alignment.  QGTC_PACK_ROW=word|shfl forces one.
         static const int force = [] { const char* e = getenv("QGTC_PACK_ROW"); return !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 's' ? 2 : 0)); }();
         const long long word_units = (long long)rows * ((wpr + 31) / 32);     // warp-level units of the word kernel: (row, 32 output words)
-        bool use_word = vec && nbits >= 3 && W >= 1024 && word_units >= 2ll * kNumSMs * 8;
+        bool use_word = vec && W >= 1024 && word_units >= 2ll * kNumSMs * 8;
         if (force == 1) use_word = vec;
         if (force == 2) use_word = false;
         if (use_word) {
             const int grid = grid_for((word_units + 7) / 8, 8);
+            const int vec8 = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) & 31u) == 0) ? 1 : 0;
 #define QGTC_PACK_ROW(NB) \
-    case NB: pack_row_kernel<NB, true><<<grid, 256, 0, st>>>(in, H, W, out); break;
+    case NB: pack_row_kernel<NB, true><<<grid, 256, 0, st>>>(in, H, W, out, vec8); break;
             switch (nbits) {
                 QGTC_PACK_ROW(1) QGTC_PACK_ROW(2) QGTC_PACK_ROW(3) QGTC_PACK_ROW(4)
                 QGTC_PACK_ROW(5) QGTC_PACK_ROW(6) QGTC_PACK_ROW(7) QGTC_PACK_ROW(8)
