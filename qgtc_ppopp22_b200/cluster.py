@@ -92,6 +92,37 @@ def make_small_graph_batches(num_graphs: int = 1024, graphs_per_batch: int = 32,
                           num_classes, parts)
 
 
+def get_partition_list(g: "SyntheticGraph", psize: int):
+    """partition_utils.py:11-18: the list of node-id arrays, one per partition.  The reference asks METIS (dgl.transform.
+    metis_partition); DGL is not installable offline, so the synthetic graph carries its planted partition, which plays METIS's
+    output.  A real partitioner plugs in here."""
+    return [np.asarray(p, dtype=np.int64) for p in list(g.parts)[:psize]]
+
+
+def cached_partition_list(dn, g: "SyntheticGraph", psize: int, cache_dir: str = "./datasets/"):
+    """sampler.py:56-65: partitions of a named dataset are cached as ``./datasets/{name}_{psize}.npy`` -- an object array of
+    node-id arrays written with np.save and read back with np.load(allow_pickle=True), the reference's own format -- so a cache
+    produced by the reference (METIS partitions of the real datasets) is picked up unchanged.  dn = None / '' disables the cache."""
+    import os
+    if not dn:
+        return get_partition_list(g, psize)
+    fn = os.path.join(cache_dir, dn + "_{}.npy".format(psize))
+    if os.path.exists(fn):
+        par = np.load(fn, allow_pickle=True)
+        par_li = [np.asarray(p, dtype=np.int64) for p in par]
+        n_nodes = sum(len(p) for p in par_li)
+        if len(par_li) == psize and n_nodes <= g.num_nodes and (n_nodes == 0 or max(int(p.max()) for p in par_li if len(p)) < g.num_nodes):
+            return par_li
+        # a stale cache of another graph: fall through and rewrite it
+    os.makedirs(cache_dir, exist_ok=True)
+    par_li = get_partition_list(g, psize)
+    arr = np.empty(len(par_li), dtype=object)
+    for i, p_ in enumerate(par_li):
+        arr[i] = p_
+    np.save(fn, arr)
+    return par_li
+
+
 class ClusterTensor(torch.nn.Module):
     """sampler.py:12-19: a container of the two packed buffers that moves with .cuda()/.cpu()."""
 
@@ -119,7 +150,7 @@ class ClusterIter:
 
     def __init__(self, dn, g: SyntheticGraph, psize, batch_size, seed_nid=None, use_pp=False, regular=False,
                  bit_width=2, run_GIN=False, device=None, batch_ids=None, keep_on_cpu=False, ops=None, par_li=None,
-                 from_edges=False, tile_bitmaps=False):
+                 from_edges=False, tile_bitmaps=False, partition_cache=False):
         self.g = g
         self.psize = psize
         self.batch_size = batch_size
@@ -127,7 +158,7 @@ class ClusterIter:
         self.regular = regular
         self.max = int(psize // batch_size)
         if par_li is None:
-            self.par_li = list(g.parts)[:psize]
+            self.par_li = cached_partition_list(dn if partition_cache else None, g, psize)    # sampler.py:56-65
             random.shuffle(self.par_li)                   # sampler.py:68 (random.seed(2) set by the driver)
         else:
             self.par_li = list(par_li)                    # already shuffled (multi-rank runs share one order)
@@ -204,9 +235,10 @@ class ClusterIter:
         raise StopIteration
 
 
-def shuffled_partitions(g: SyntheticGraph, psize: int):
-    """The partition order every rank must agree on (sampler.py:68 after main_qgtc.py:47's random.seed(2))."""
-    par_li = list(g.parts)[:psize]
+def shuffled_partitions(g: SyntheticGraph, psize: int, cache_name=None):
+    """The partition order every rank must agree on (sampler.py:68 after main_qgtc.py:47's random.seed(2)).  `cache_name` turns
+    on the reference's partition cache (./datasets/{name}_{psize}.npy, sampler.py:56-65)."""
+    par_li = cached_partition_list(cache_name, g, psize)
     random.Random(2).shuffle(par_li)
     return par_li
 

@@ -50,6 +50,7 @@ def build_parser():
     p.add_argument("--tile-bitmap", choices=["auto", "on", "off"], default="auto",
                    help="--grouped: pass the batches' tile bitmaps (zero-tile jumping); auto = when under half of the tiles are non-zero")
     p.add_argument("--min-region-ms", type=float, default=0.0, help="--cuda-graph: replay enough epochs for a timed region of at least this many ms")
+    p.add_argument("--partition-cache", action="store_true", help="cache the partition list as ./datasets/{dataset}_{psize}.npy like sampler.py:56-65")
     p.add_argument("--gather-logits", action="store_true", help="after the timed epochs, all_gather every batch's logits to all ranks (NCCL)")
     p.add_argument("--dense-pack", action="store_true", help="build batches through the dense fp32 n x n adjacency as sampler.py:87-89 does "
                                                               "(default: packed straight from the edge list)")
@@ -143,7 +144,11 @@ def run(args, graph=None, quiet=False, ops=None):
         else:
             known = args.dataset in C.SHAPES
             graph = C.make_synthetic_graph(args.dataset, args.psize, dim=None if known else args.dim)
-    par_li = C.shuffled_partitions(graph, args.psize)
+    par_li = C.shuffled_partitions(graph, args.psize, args.dataset if getattr(args, "partition_cache", False) and (rank == 0 or world == 1) else None)
+    if world > 1 and getattr(args, "partition_cache", False):      # rank 0 wrote / read the cache; the others read it after the barrier
+        import torch.distributed as dist
+        dist.barrier()
+        par_li = C.shuffled_partitions(graph, args.psize, args.dataset)
     counts = C.batch_node_counts(par_li, args.psize, args.batch_size)
     shards = C.shard_batches([float(n) * n for n in counts], world)      # dominant cost ~ n^2 * hidden
     it = C.ClusterIter(args.dataset, graph, args.psize, args.batch_size, None, use_pp=False, regular=args.regular,

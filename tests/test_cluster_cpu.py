@@ -42,6 +42,26 @@ def test_shard_batches_covers_and_balances(world):
     assert max(loads) <= 1.25 * (sum(costs) / world)
 
 
+def test_partition_cache_uses_the_reference_format(tmp_path):
+    """sampler.py:56-65: ./datasets/{name}_{psize}.npy, an object array read with np.load(allow_pickle=True)."""
+    g = C.make_synthetic_graph("tiny", 60)
+    d = str(tmp_path) + "/"
+    first = C.cached_partition_list("tiny", g, 60, cache_dir=d)
+    fn = os.path.join(d, "tiny_60.npy")
+    assert os.path.exists(fn)
+    raw = np.load(fn, allow_pickle=True)                                 # exactly what the reference does
+    assert raw.dtype == object and len(raw) == 60 and all(np.array_equal(a, b) for a, b in zip(raw, first))
+    # a cache written by someone else (e.g. METIS partitions from the reference) is picked up unchanged
+    other = np.empty(60, dtype=object)
+    perm = np.random.default_rng(1).permutation(g.num_nodes)
+    for i in range(60):
+        other[i] = perm[i * 50:(i + 1) * 50].astype(np.int64)
+    np.save(fn, other)
+    again = C.cached_partition_list("tiny", g, 60, cache_dir=d)
+    assert all(np.array_equal(a, b) for a, b in zip(again, other))
+    assert len(C.cached_partition_list(None, g, 60, cache_dir=d)) == 60   # no name: no cache
+
+
 def test_small_graph_batches():
     g = C.make_small_graph_batches(num_graphs=64)
     assert len(g.parts) == 64 and all(16 <= len(p) <= 64 for p in g.parts)
