@@ -196,6 +196,22 @@ typedef enum qgtc_group_kind { QGTC_GROUP_BITS_ROW = 0, QGTC_GROUP_FLOAT = 1, QG
 int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,
                        int kind, int pad128, int engine, unsigned flags, void* stream);
 
+/* Fused aggregation + update: for every problem  out2 = op2( bitMM2Bit(X1, X2) , W )  in ONE launch -- the pairs
+ * main_qgtc.py:148+150, :152+153 (GCN) and :131+132, :133+134, :135+136 (GIN).  The first op is bitMM2Bit (result R(out_bit, M, N),
+ * N <= 64); its requantized tile goes straight back into tensor memory as the A operand of the second op, which is
+ * bitMM2Bit(o, W, M, N, N2, out_bit, bit_w, out_bit2) (kind2 = QGTC_GROUP_BITS_ROW) or bitMM2Int(o, W, M, N, N2, out_bit, bit_w, pad128)
+ * (kind2 = QGTC_GROUP_FLOAT) with one weight matrix W = C(bit_w, N, N2) shared by all problems (N2 <= 128).  out2 is bit-identical
+ * to the two separate calls.  problems[i].out_dev / out_size are only used when write_out1 != 0 (the first op's own result is then
+ * written as well).  Returns QGTC_ERR_UNSUPPORTED when the shapes do not fit (the caller then issues the two ops separately). */
+typedef struct qgtc_fused_update {
+    const int32_t* w_dev;
+    size_t w_words;
+    int N2, bit_w, out_bit2, kind2, pad128;
+} qgtc_fused_update;
+int qgtc_bitmm_grouped_fused(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,
+                             const qgtc_fused_update* upd, void* const* out2_dev, const size_t* out2_size, int write_out1,
+                             int engine, unsigned flags, void* stream);
+
 /* Number of kernels this library has launched from the calling process (bench.py gpu_launches). */
 uint64_t qgtc_launch_count(void);
 

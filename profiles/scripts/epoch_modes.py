@@ -20,7 +20,7 @@ else:
     g = C.make_synthetic_graph(which, 1500)
     base = ["--dataset", which, "--use_QGTC", "--n-classes", str(g.num_classes)]
 MODES = {"eager": [], "graph": ["--cuda-graph"], "graph_16streams": ["--cuda-graph", "--streams", "16"],
-         "grouped_eager": ["--grouped"], "grouped_graph": ["--grouped", "--cuda-graph"],
+         "grouped_eager": ["--grouped"], "grouped_graph": ["--grouped", "--cuda-graph"], "grouped_graph_unfused": ["--grouped", "--cuda-graph", "--no-fuse"],
          "grouped_graph_nomaps": ["--grouped", "--cuda-graph", "--tile-bitmap", "off"], "grouped_graph_maps": ["--grouped", "--cuda-graph", "--tile-bitmap", "on"]}
 for b in bits:
     row = {"graph": which, "bits": b}

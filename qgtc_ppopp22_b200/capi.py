@@ -26,6 +26,7 @@ SYMBOLS = [
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
     "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit", "qgtc_bitmm_grouped", "qgtc_bitmm2bit_host_batched_multi",
+    "qgtc_bitmm_grouped_fused",
 ]
 
 
@@ -33,6 +34,12 @@ class HostVariant(ctypes.Structure):
     """qgtc_host_variant (include/qgtc_b200.h)."""
     _fields_ = [("x2_host", ctypes.c_void_p), ("x2_stride_words", ctypes.c_size_t), ("bit2", ctypes.c_int), ("out_bit", ctypes.c_int),
                 ("out_host", ctypes.c_void_p), ("out_stride_words", ctypes.c_size_t)]
+
+
+class FusedUpdate(ctypes.Structure):
+    """qgtc_fused_update (include/qgtc_b200.h)."""
+    _fields_ = [("w_dev", ctypes.c_void_p), ("w_words", ctypes.c_size_t), ("N2", ctypes.c_int), ("bit_w", ctypes.c_int),
+                ("out_bit2", ctypes.c_int), ("kind2", ctypes.c_int), ("pad128", ctypes.c_int)]
 
 
 class GroupProblem(ctypes.Structure):
@@ -86,6 +93,8 @@ def lib() -> ctypes.CDLL:
         L.qgtc_bitmm2bit_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2int_tilemap.argtypes = [vp, sz, vp, sz, vp, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2bit_host_batched_multi.argtypes = [vp, sz, i, i, i, i, i, c.POINTER(HostVariant), i, i, c.c_uint, vp]
+        L.qgtc_bitmm_grouped_fused.argtypes = [c.POINTER(GroupProblem), i, i, i, i, i, c.POINTER(FusedUpdate), c.POINTER(c.c_void_p),
+                                               c.POINTER(c.c_size_t), i, i, c.c_uint, vp]
         L.qgtc_bitmm_grouped.argtypes = [c.POINTER(GroupProblem), i, i, i, i, i, i, i, i, c.c_uint, vp]
         _LIB = L
     return _LIB
@@ -360,3 +369,47 @@ def bitMM2Bit_host_batched_multi(x1_host, x2_hosts, count, M, K, N, bit1, bit2s,
     _check(lib().qgtc_bitmm2bit_host_batched_multi(x1_host.data_ptr(), x1_host.shape[1], count, M, K, N, bit1, arr, nvar, engine, flags, _stream()),
            "bitMM2Bit_host_batched_multi")
     return out_hosts
+
+
+def bitmm_grouped_fused(x1s, x2s, Ms, Ks, N, bit1, bit2, out_bit, W, N2, bit_w, out_bit2, kind2=GROUP_BITS_ROW, pad_128=False,
+                        tile_maps=None, write_out1=False, engine=ENGINE_AUTO, flags=0):
+    """Fused aggregation + update in one launch (qgtc_bitmm_grouped_fused): for every problem
+    out2 = op2(bitMM2Bit(x1, x2, M, K, N, bit1, bit2, out_bit), W) with op2 = bitMM2Bit(o, W, M, N, N2, out_bit, bit_w, out_bit2)
+    (kind2 = GROUP_BITS_ROW) or bitMM2Int(o, W, M, N, N2, out_bit, bit_w, pad_128) (GROUP_FLOAT).  Returns (outs2, outs1 or None)."""
+    count = len(x1s)
+    if not (count == len(x2s) == len(Ms) == len(Ks)) or count == 0:
+        raise QgtcError("bitmm_grouped_fused: operand lists must be non-empty and of equal length")
+    _req_cuda(W, torch.int32, "bit_W")
+    dev = x1s[0].device
+    arr = (GroupProblem * count)()
+    out2_ptrs, out2_sizes = (ctypes.c_void_p * count)(), (ctypes.c_size_t * count)()
+    if kind2 == GROUP_FLOAT:
+        shapes2, dtype2 = [(int(m), N2) for m in Ms], torch.float32
+    else:
+        shapes2, dtype2 = [packed_shape(LAYOUT_ROW, out_bit2, int(m), N2) for m in Ms], torch.int32
+    shapes1 = [packed_shape(LAYOUT_ROW, out_bit, int(m), N) for m in Ms]
+
+    def alloc(shapes, dtype):
+        offs, total = [], 0
+        for a, b in shapes:
+            offs.append(total)
+            total += (a * b + 3) & ~3
+        flat = torch.empty((total,), dtype=dtype, device=dev)
+        return [flat[o:o + a * b].view((a, b)) for o, (a, b) in zip(offs, shapes)]
+
+    with torch.cuda.device(dev):
+        outs2 = alloc(shapes2, dtype2)
+        outs1 = alloc(shapes1, torch.int32) if write_out1 else None
+        for k in range(count):
+            a, b = x1s[k], x2s[k]
+            _req_cuda(a, torch.int32, "bit_X1[%d]" % k); _req_cuda(b, torch.int32, "bit_X2[%d]" % k)
+            p = arr[k]
+            p.x1_dev, p.x1_words, p.x2_dev, p.x2_words = a.data_ptr(), a.numel(), b.data_ptr(), b.numel()
+            p.out_dev, p.out_size = (outs1[k].data_ptr(), outs1[k].numel()) if write_out1 else (None, 0)
+            p.tile_bitmap_dev = tile_maps[k].data_ptr() if tile_maps is not None and tile_maps[k] is not None else None
+            p.M, p.K = int(Ms[k]), int(Ks[k])
+            out2_ptrs[k], out2_sizes[k] = outs2[k].data_ptr(), outs2[k].numel()
+        upd = FusedUpdate(W.data_ptr(), W.numel(), N2, bit_w, out_bit2, kind2, int(bool(pad_128)))
+        _check(lib().qgtc_bitmm_grouped_fused(arr, count, N, bit1, bit2, out_bit, ctypes.byref(upd), out2_ptrs, out2_sizes, int(bool(write_out1)),
+                                              engine, flags, _stream()), "bitmm_grouped_fused")
+    return outs2, outs1

@@ -29,10 +29,17 @@ struct GroupedProblemHost {
     const uint32_t* bitmap;
     unsigned long long x1_words, x2_words;
     int M, K;
+    void* out2;
+};
+struct GroupedFusedHost {
+    const uint32_t* w;
+    unsigned long long w_words;
+    int N2, bit_w, out_bit2, epi2, pad128_2, write_out1;
 };
 bool grp_supports(int N, int bit1, int bit2, int epi);
+bool grp_supports_fused(int N, int bit1, int bit2, int N2, int bit_w, int epi2);
 int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int bit1, int bit2, int out_bit, int epi, int pad128,
-                        unsigned flags, cudaStream_t st);
+                        unsigned flags, cudaStream_t st, const GroupedFusedHost* fu = nullptr);
 
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_cuda_err[256] = "";
@@ -99,7 +106,7 @@ static int fill_gemm_args(GemmArgs& a, const int32_t* x1, size_t x1_words, const
 // one problem (or a uniform batch that the batch engine refused) on the grouped engine
 static int run_grouped_single(const GemmArgs& a, int epi, cudaStream_t st) {
     if (a.count != 1) return QGTC_ERR_UNSUPPORTED;
-    GroupedProblemHost h{a.x1, a.x2, a.out, a.tile_bitmap, a.x1_words, a.x2_words, a.M, a.K};
+    GroupedProblemHost h{a.x1, a.x2, a.out, a.tile_bitmap, a.x1_words, a.x2_words, a.M, a.K, nullptr};
     const int pad128 = a.w_offset == (unsigned long long)a.gdk * 4 * p128(a.N) ? 1 : 0;
     return launch_gemm_grouped(&h, 1, a.N, a.bit1, a.bit2, a.out_bit, epi, pad128, a.flags, st);
 }
@@ -523,7 +530,7 @@ int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N
         for (int i = 0; i < count; ++i) {
             const qgtc_group_problem& p = problems_host[i];
             v[(size_t)i] = GroupedProblemHost{reinterpret_cast<const uint32_t*>(p.x1_dev), reinterpret_cast<const uint32_t*>(p.x2_dev), p.out_dev,
-                                              p.tile_bitmap_dev, (unsigned long long)p.x1_words, (unsigned long long)p.x2_words, p.M, p.K};
+                                              p.tile_bitmap_dev, (unsigned long long)p.x1_words, (unsigned long long)p.x2_words, p.M, p.K, nullptr};
         }
         const int rc = launch_gemm_grouped(v.data(), count, N, bit1, bit2, out_bit, epi, pad128, flags, st);
         if (rc != QGTC_ERR_UNSUPPORTED) return rc;
@@ -548,6 +555,40 @@ int qgtc_bitmm_grouped(const qgtc_group_problem* problems_host, int count, int N
         if (rc != QGTC_OK) return rc;
     }
     return QGTC_OK;
+}
+
+int qgtc_bitmm_grouped_fused(const qgtc_group_problem* problems_host, int count, int N, int bit1, int bit2, int out_bit,
+                             const qgtc_fused_update* upd, void* const* out2_dev, const size_t* out2_size, int write_out1,
+                             int engine, unsigned flags, void* stream) {
+    if (!problems_host || !upd || !out2_dev || !out2_size || count <= 0 || N <= 0 || !upd->w_dev || upd->N2 <= 0) return QGTC_ERR_INVALID_ARG;
+    if (upd->kind2 != QGTC_GROUP_BITS_ROW && upd->kind2 != QGTC_GROUP_FLOAT) return QGTC_ERR_INVALID_ARG;
+    if (!bits_ok(bit1) || !bits_ok(bit2) || !bits_ok(out_bit) || !bits_ok(upd->bit_w)) return QGTC_ERR_UNSUPPORTED;
+    if (upd->kind2 == QGTC_GROUP_BITS_ROW && !bits_ok(upd->out_bit2)) return QGTC_ERR_UNSUPPORTED;
+    if (!flags_ok(flags)) return QGTC_ERR_INVALID_ARG;
+    if (!aligned16(upd->w_dev)) return QGTC_ERR_ALIGNMENT;
+    const int epi2 = upd->kind2 == QGTC_GROUP_BITS_ROW ? kEpiBitsRow : kEpiFloat;
+    for (int i = 0; i < count; ++i) {
+        const qgtc_group_problem& p = problems_host[i];
+        if (!p.x1_dev || !p.x2_dev || !out2_dev[i] || p.M <= 0 || p.K <= 0 || (write_out1 && !p.out_dev)) return QGTC_ERR_INVALID_ARG;
+        if (!aligned16(p.x1_dev) || !aligned16(p.x2_dev) || !aligned16(out2_dev[i]) || (write_out1 && !aligned16(p.out_dev))) return QGTC_ERR_ALIGNMENT;
+        if ((long long)p8(p.M) * s128(p.K) * 4 * 8 > (1ll << 40)) return QGTC_ERR_UNSUPPORTED;
+        if (write_out1 && p.out_size < qgtc_packed_words(QGTC_LAYOUT_ROW, out_bit, p.M, N)) return QGTC_ERR_SIZE;
+        const size_t need2 = epi2 == kEpiFloat ? (size_t)p.M * upd->N2 : qgtc_packed_words(QGTC_LAYOUT_ROW, upd->out_bit2, p.M, upd->N2);
+        if (out2_size[i] < need2) return QGTC_ERR_SIZE;
+    }
+    if (int rc = check_device()) return rc;
+    if (engine == QGTC_ENGINE_MMA_SYNC || engine == QGTC_ENGINE_TCGEN05) return QGTC_ERR_UNSUPPORTED;
+    if (!grp_supports(N, bit1, bit2, kEpiBitsRow) || !grp_supports_fused(N, bit1, bit2, upd->N2, upd->bit_w, epi2)) return QGTC_ERR_UNSUPPORTED;
+    static thread_local std::vector<GroupedProblemHost> v;
+    v.resize((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        const qgtc_group_problem& p = problems_host[i];
+        v[(size_t)i] = GroupedProblemHost{reinterpret_cast<const uint32_t*>(p.x1_dev), reinterpret_cast<const uint32_t*>(p.x2_dev), write_out1 ? p.out_dev : nullptr,
+                                          p.tile_bitmap_dev, (unsigned long long)p.x1_words, (unsigned long long)p.x2_words, p.M, p.K, out2_dev[i]};
+    }
+    const GroupedFusedHost fu{reinterpret_cast<const uint32_t*>(upd->w_dev), (unsigned long long)upd->w_words, upd->N2, upd->bit_w,
+                              epi2 == kEpiFloat ? 1 : upd->out_bit2, epi2, upd->pad128 ? 1 : 0, write_out1 ? 1 : 0};
+    return launch_gemm_grouped(v.data(), count, N, bit1, bit2, out_bit, kEpiBitsRow, 1, flags, (cudaStream_t)stream, &fu);
 }
 
 uint64_t qgtc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

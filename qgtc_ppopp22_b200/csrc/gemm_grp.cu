@@ -44,7 +44,8 @@ constexpr int kConvWarp0 = kEpiWarp0 + 4;
 constexpr int kConvWarps = 4;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kIssuerWarp = kConvWarp0 + kConvWarps;
-constexpr int kThreads = (kIssuerWarp + 1) * 32;   // 544
+constexpr int kIssuer2Warp = kIssuerWarp + 1;      // fused update GEMM (second tcgen05.mma chain); idle otherwise
+constexpr int kThreads = (kIssuer2Warp + 1) * 32;  // 576
 constexpr int kARing = 3;                     // staged pipeline items per expander warp (cp.async groups in flight)
 constexpr int kMaxBRing = 4;                  // ... per converter thread: 2..4 by shared-memory budget (GrpArgs::b_ring)
 constexpr int kMaxTasks = 2;                  // (chunk, column) conversion tasks per converter thread and item: cps * NP <= 256
@@ -64,8 +65,11 @@ struct GrpProblem {
     int M, K;
     int unit0;                                // index of this problem's first work unit
     int mt;                                   // (per-CTA unit records only) the unit's 128-row tile
+    void* out2;                               // fused update: the second op's output of this problem
+    unsigned long long pad_;
 };
-static_assert(sizeof(GrpProblem) == 64, "problem descriptors are 64 bytes");
+static_assert(sizeof(GrpProblem) == 80, "problem descriptors are 80 bytes");
+constexpr int kDescWords = (int)(sizeof(GrpProblem) / 4);
 
 struct GrpArgs {
     int count, units;
@@ -77,6 +81,11 @@ struct GrpArgs {
     unsigned flags;
     unsigned int* error_flag;
     unsigned long long* trace;                // clock64 trace buffer (debug instance only), else null
+    // fused update GEMM (0 = off): every unit's requantized tile (A2, K2 = N <= 64) times one shared weight matrix W
+    int fused, N2, NP2, bit_w, out_bit2, epi2, pad128_2, write_out1;
+    int a2_col, d2_col, off_b2;               // TMEM columns of the A2 operand / the second accumulator, smem offset of W's image
+    const uint32_t* w2;
+    unsigned long long w2_words;
     GrpProblem p[kGrpMaxProblems];
     unsigned short unit_z[kUnitTable];        // problem of unit u (valid when units <= kUnitTable)
 };
@@ -108,8 +117,10 @@ struct UnitRec {
     const uint32_t* bm;                       // bitmap words of this tile, or null
     unsigned long long x1_words, x2_words;
     int M, gdk, mt, item0;                    // rows, K chunks, 128-row tile, first item of the unit
+    void* out2;                               // fused update: second output
+    unsigned long long pad_;
 };
-static_assert(sizeof(UnitRec) == 64, "unit records are 64 bytes");
+static_assert(sizeof(UnitRec) == sizeof(GrpProblem), "a unit record is built in place of the copied descriptor");
 struct ItemRec {
     int c0;                                   // first K chunk
     unsigned short unit;                      // index into the unit records
@@ -223,6 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     uint64_t* empty = bars + kMaxStagesG;          // [kMaxStagesG] MMA commit -> expanders, converters
     uint64_t* d_full = bars + 2 * kMaxStagesG;     // [2] MMA commit -> epilogue
     uint64_t* d_empty = d_full + 2;                // [2] 4 epilogue warps -> MMA
+    uint64_t* a2_full = d_empty + 2;               // fused update: 4 epilogue warps wrote the A2 operand -> second issuer
+    uint64_t* d2_full = a2_full + 1;               //               second MMA chain done -> epilogue
+    uint64_t* b2_ready = d2_full + 1;              //               converters built W's image (once)
     volatile unsigned char* flags = smem + T.off_flags;   // [stage][chunk][lane quarter]: that 32 x 128-bit block has a one
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.off_misc);
     int* n_items_slot = reinterpret_cast<int*>(smem + T.off_misc + 8);
@@ -243,6 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], 4);
         }
+        mbar_init(a2_full, 4);
+        mbar_init(d2_full, 1);
+        mbar_init(b2_ready, kConvWarps);
         fence_mbar_init();
     }
     if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 512);
@@ -269,12 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             z = lo;
         }
         uint32_t* raw = reinterpret_cast<uint32_t*>(&units[k]);
-        if (lane < 16) raw[lane] = reinterpret_cast<const uint32_t*>(&T.p[z])[lane];
+        if (lane < kDescWords) raw[lane] = reinterpret_cast<const uint32_t*>(&T.p[z])[lane];
         __syncwarp();
         if (lane == 0) {
             const GrpProblem P = *reinterpret_cast<const GrpProblem*>(raw);
             UnitRec r;
-            r.x1 = P.x1; r.x2 = P.x2; r.out = P.out;
+            r.x1 = P.x1; r.x2 = P.x2; r.out = P.out; r.out2 = P.out2; r.pad_ = 0;
             r.x1_words = P.x1_words; r.x2_words = P.x2_words;
             r.M = P.M;
             r.gdk = s128(P.K);
@@ -461,6 +478,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(kConvThreads) : "memory");     // the four converter warps only
         if (!(T.flags & QGTC_FLAG_X2_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");
+        if (T.fused) {
+            // Fused update: the shared weight matrix W (packed C(bit_w, K2 = N, N2), one K chunk) -> the same u8 core-matrix
+            // image as a B stage, once per CTA.  One column per thread, staged through ring slot 0 (free until the main loop).
+            const int p8n2 = p8(T.N2), pn2 = (T.epi2 == kEpiFloat && !T.pad128_2) ? p8n2 : p128(T.N2);
+            const unsigned long long w_off2 = 4ull * (unsigned long long)pn2;          // S128(K2) == 1
+            unsigned char* st0 = b_ring + t * 16;
+            if (t < T.NP2) {
+                for (int qq = 0; qq < T.bit_w; ++qq) {
+                    const unsigned long long idx = (unsigned long long)qq * w_off2 + 4ull * t;
+                    const int nb = t < p8n2 ? piece_bytes(idx, T.w2_words) : 0;
+                    cp_async16_zfill(st0 + qq * (kConvThreads * 16), nb ? (const void*)(T.w2 + idx) : (const void*)T.w2, nb);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            if (t < T.NP2) {
+                uint32_t o[32];
+                assemble_planes_rt<false>(T.bit_w, st0, kConvThreads * 16, o);
+                unsigned char* dstc = smem + T.off_b2 + (size_t)(t >> 3) * 128 + (t & 7) * 16;
+#pragma unroll
+                for (int kg = 0; kg < 8; ++kg)
+                    *reinterpret_cast<uint4*>(dstc + (size_t)kg * (T.NP2 / 8) * 128) = make_uint4(o[4 * kg], o[4 * kg + 1], o[4 * kg + 2], o[4 * kg + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b2_ready);
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kConvThreads) : "memory");     // slot 0 is re-used by the main loop's first item
+        }
         unsigned char* ring = b_ring + t * 16;                         // piece (i, plane) of this thread at + (i * bit2 + plane) * 2048
         const bool tr = TRACE && warp == kConvWarp0 && tlane;
         if (tr) QGTC_GTRACE(2, 20);
@@ -581,6 +626,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 if (++buf == T.dbufs) { buf = 0; ++duse; }
             }
         }
+    } else if (warp == kIssuer2Warp) {
+        // ===================== second issuer: the fused update GEMM D2 = A2 x W, one chain per unit =====================
+        if (T.fused) {
+            const int NP2 = T.NP2;
+            const uint32_t idesc2 = make_idesc_i8(NP2, 128);
+            const uint32_t lbo2 = (uint32_t)(NP2 / 8) * 128u;
+            const uint64_t desc2 = make_smem_desc(smem_u32(smem + T.off_b2), lbo2, 128u);
+            const uint32_t desc2_hi = (uint32_t)(desc2 >> 32), desc2_lo = (uint32_t)desc2, kstep2 = (2u * lbo2) >> 4;
+            const int nk2 = (T.N + 31) >> 5;                 // K2 = N <= 64: one or two MMAs of K = 32
+            gwait(b2_ready, 0, ef, 20);
+#pragma unroll 1
+            for (int tl = 0; tl < units_here; ++tl) {
+                gwait(a2_full, (uint32_t)tl & 1, ef, 21);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int ks = 0; ks < nk2; ++ks) {
+                        const uint64_t desc = ((uint64_t)desc2_hi << 32) | (uint64_t)(desc2_lo + (uint32_t)ks * kstep2);
+                        mma_i8_ts(tmem_base + (uint32_t)T.d2_col, tmem_base + (uint32_t)(T.a2_col + 8 * ks), desc, idesc2, ks > 0 ? 1u : 0u);
+                    }
+                    tc_commit(d2_full);
+                }
+                __syncwarp();
+            }
+        }
     } else {
         // ===================== epilogue (4 warps: one per TMEM lane quarter) =====================
         const int q = warp & 3;
@@ -599,6 +668,113 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             tc_fence_after();
             if (tr) QGTC_GTRACE(4, 41);
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
+            if (T.fused) {
+                // ---- stage 1: requantized bytes of this row (natural order: register j = columns 4j .. 4j+3), NP <= 64
+                const bool row_ok = m < p8(M);
+                const uint32_t rmask = m < M ? 0xffffffffu : 0u;
+                const unsigned keep = (1u << ob) - 1u;
+                const int mx = 1 << ob;
+                uint32_t nat[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) nat[j] = 0u;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    if (16 * cb < NP) {
+                        int v[16];
+                        tmem_ld16(d_tmem + 16 * cb, v);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            uint32_t four = (mode2 && ob <= 4)
+                                                ? requant4<true, true>(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3], dshift, ob, mx, keep)
+                                                : requant4<false, false>(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3], dshift, ob, mx, keep);
+                            const int nv = N - (16 * cb + 4 * g4);       // valid columns of this group of four
+                            const uint32_t mask = nv >= 4 ? rmask : (nv <= 0 ? 0u : (rmask & ((1u << (8 * nv)) - 1u)));
+                            nat[4 * cb + g4] = four & mask;
+                        }
+                    }
+                }
+                if (T.write_out1 && row_ok) {        // the first op's own result R(ob, M, N), when the caller wants it
+                    uint32_t* out = reinterpret_cast<uint32_t*>(P.out);
+                    const int wpr = s128(N) * 4;
+                    const unsigned long long opt_offset = (unsigned long long)p8(M) * wpr;
+                    for (int p = 0; p < ob; ++p) {
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+                            if (32 * w < NP) {
+                                uint32_t word = 0u;
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) word |= nibble_of_plane(nat[8 * w + g], p) << (28 - 4 * g);
+                                out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = word;
+                            }
+                        }
+                        for (int w = (NP + 31) / 32; w < wpr; ++w) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = 0u;
+                    }
+                }
+                // ---- A2 operand: byte i of register 8 s + c = value of column 32 s + c + 8 i (the K permutation W's image uses)
+                uint32_t a2[16];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll
+                    for (int cq = 0; cq < 2; ++cq) {
+                        const uint32_t r0 = nat[8 * s2 + cq], r1 = nat[8 * s2 + cq + 2], r2 = nat[8 * s2 + cq + 4], r3 = nat[8 * s2 + cq + 6];
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt) {
+                            const uint32_t sel = (uint32_t)(tt | ((4 + tt) << 4));
+                            a2[8 * s2 + 4 * cq + tt] = __byte_perm(__byte_perm(r0, r1, sel), __byte_perm(r2, r3, sel), 0x5410u);
+                        }
+                    }
+                }
+                const uint32_t a2_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)T.a2_col;
+                if (N > 32) tmem_st16r(a2_tmem, a2);
+                else tmem_st8(a2_tmem, a2);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a2_full);            // -> second issuer
+                    mbar_arrive(&d_empty[buf]);      // the main accumulator is drained
+                }
+                // ---- stage 2: the update GEMM's accumulator -> second output
+                gwait(d2_full, (uint32_t)tl & 1, ef, 22);
+                tc_fence_after();
+                const int N2 = T.N2, NP2 = T.NP2, ob2 = T.out_bit2;
+                const uint32_t d2_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)T.d2_col;
+                if (T.epi2 == kEpiFloat) {
+                    float* out2 = reinterpret_cast<float*>(P.out2);
+                    for (int cb = 0; cb < NP2 / 16; ++cb) {
+                        int v[16];
+                        tmem_ld16(d2_tmem + 16 * cb, v);
+                        if (m < M) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int n = 16 * cb + j;
+                                if (n < N2) out2[(size_t)m * N2 + n] = (float)v[j];
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t* out2 = reinterpret_cast<uint32_t*>(P.out2);
+                    const int wpr2 = s128(N2) * 4;
+                    const unsigned long long opt2 = (unsigned long long)p8(M) * wpr2;
+                    uint32_t* out2_row = out2 + (unsigned long long)m * wpr2;
+                    switch (ob2) {
+                        case 1: epi_bits_tile<1, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
+                        case 2: epi_bits_tile<2, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
+                        case 4: epi_bits_tile<4, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
+                        case 8: epi_bits_tile<8, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
+                        default: epi_bits_tile<0, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
+                    }
+                    if (row_ok) {
+                        for (int w = (NP2 + 31) / 32; w < wpr2; ++w)
+                            for (int p = 0; p < ob2; ++p) out2[(unsigned long long)p * opt2 + (unsigned long long)m * wpr2 + w] = 0u;
+                    }
+                }
+                tc_fence_before();               // D2 / A2 are free again once all four warps have passed (next unit's a2_full)
+                __syncwarp();
+                if (tr) QGTC_GTRACE(4, 42);
+                if (++buf == T.dbufs) { buf = 0; ++duse; }
+                continue;
+            }
             if (T.epi == kEpiFloat) {
                 float* out = reinterpret_cast<float*>(P.out);
                 for (int cb = 0; cb < NP / 16; ++cb) {
@@ -689,30 +865,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 
 struct GrpPlan {
     int NP, cps, stages, dbufs, groups, a_slot, b_slot, b_stage, b_ring, off_bstage, off_bring, off_bars, off_flags, off_misc, off_units, smem_total;
+    int NP2, a2_col, d2_col, off_b2;      // fused update (NP2 == 0: none)
 };
 
-// pipeline geometry for (N, bit1, bit2); false when the shape does not fit this engine
-bool plan_for(int N, int bit1, int bit2, GrpPlan& pl) {
+// pipeline geometry for (N, bit1, bit2) and, with N2 > 0, a fused update GEMM of width N2 with bit_w weight planes; false when
+// the shape does not fit this engine
+bool plan_for(int N, int bit1, int bit2, GrpPlan& pl, int N2 = 0, int bit_w = 0) {
     pl.NP = ((p8(N) + 15) / 16) * 16;
     if (pl.NP > 256 || bit1 < 1 || bit1 > 8 || bit2 < 1 || bit2 > 8) return false;
+    pl.NP2 = N2 > 0 ? ((p8(N2) + 15) / 16) * 16 : 0;
+    if (N2 > 0 && (pl.NP > 64 || pl.NP2 > 128 || bit_w < 1 || bit_w > 8)) return false;     // A2 = one requantized tile of K2 = N <= 64
+    const int extra_cols = N2 > 0 ? 16 + pl.NP2 : 0;      // A2 operand (16 columns) + second accumulator
     int cps = 256 / pl.NP;                       // the converters take at most kMaxTasks x 128 (chunk, column) tasks per item
     if (cps > kMaxCpsG) cps = kMaxCpsG;
     while (cps > 1 && cps * bit1 > 8) cps >>= 1; // staging: at most 8 pieces of 16 B per lane and item
     if (cps == 3) cps = 2;
     pl.cps = cps;
-    pl.dbufs = (2 * pl.NP + 2 * cps * 32 <= 512) ? 2 : 1;
+    pl.dbufs = (2 * pl.NP + 2 * cps * 32 + extra_cols <= 512) ? 2 : 1;
     for (int stages = kMaxStagesG; stages >= 2; --stages) {
-        if (pl.dbufs * pl.NP + stages * cps * 32 > 512) continue;
+        if (pl.dbufs * pl.NP + stages * cps * 32 + extra_cols > 512) continue;
+        pl.a2_col = pl.dbufs * pl.NP + stages * cps * 32;
+        pl.d2_col = pl.a2_col + 16;
         pl.stages = stages;
         pl.groups = stages < 2 ? 1 : 2;          // G <= S keeps the parity-only mbarrier waits unambiguous (see gemm_tc05.cu)
         pl.a_slot = bit1 * cps * 512;
         const int tasks_per_thread = (cps * pl.NP + kConvThreads - 1) / kConvThreads;      // 1 or 2 (cps * NP <= 256)
         pl.b_slot = tasks_per_thread * bit2 * kConvThreads * 16;
+        if (bit_w * kConvThreads * 16 > pl.b_slot) pl.b_slot = bit_w * kConvThreads * 16;   // slot 0 also stages W's planes once
         pl.b_stage = cps * pl.NP * 128;
         int off = kExpWarps * kARing * pl.a_slot;
         off = (off + 1023) & ~1023;
         pl.off_bstage = off;
         off += stages * pl.b_stage;
+        pl.off_b2 = off;                         // W's image of the fused update (one K chunk)
+        off += pl.NP2 * 128;
         pl.off_bring = off;
         // converter staging ring: as deep as shared memory allows (the converters' loads are issued b_ring - 1 items ahead;
         // two is not enough to cover the L2 / HBM latency of a short item), leaving room for the per-CTA work lists
@@ -720,7 +906,7 @@ bool plan_for(int N, int bit1, int bit2, GrpPlan& pl) {
         while (pl.b_ring > 2 && off + pl.b_ring * pl.b_slot + 512 + 24 * 1024 > 227 * 1024) --pl.b_ring;
         off += pl.b_ring * pl.b_slot;
         pl.off_bars = off;
-        off += (2 * kMaxStagesG + 4) * 8;
+        off += (2 * kMaxStagesG + 4 + 3) * 8;
         pl.off_flags = off;
         off += kMaxStagesG * kMaxCpsG * 4;
         pl.off_misc = off;
@@ -741,6 +927,12 @@ struct GroupedProblemHost {     // what the ABI layer hands over (host memory)
     const uint32_t* bitmap;
     unsigned long long x1_words, x2_words;
     int M, K;
+    void* out2;                 // fused update only
+};
+struct GroupedFusedHost {       // the second op of a fused launch: out2 = op2(requant(op1), W)
+    const uint32_t* w;
+    unsigned long long w_words;
+    int N2, bit_w, out_bit2, epi2, pad128_2, write_out1;
 };
 
 bool grp_supports(int N, int bit1, int bit2, int epi) {
@@ -748,16 +940,27 @@ bool grp_supports(int N, int bit1, int bit2, int epi) {
     GrpPlan pl;
     return plan_for(N, bit1, bit2, pl);
 }
+bool grp_supports_fused(int N, int bit1, int bit2, int N2, int bit_w, int epi2) {
+    if (epi2 != kEpiBitsRow && epi2 != kEpiFloat) return false;
+    GrpPlan pl;
+    return plan_for(N, bit1, bit2, pl, N2, bit_w);
+}
 
 unsigned long long* g_grp_trace = nullptr;     // clock64 trace buffer of the debug instance (QGTC_GRP_TRACE=1)
 constexpr size_t kGrpTraceWords = (size_t)kTraceRoles * kTraceEvents * 2;
 
 // One op over `count` problems.  Returns QGTC_ERR_UNSUPPORTED (before any work is enqueued) when the shape does not fit.
 int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int bit1, int bit2, int out_bit, int epi, int pad128,
-                        unsigned flags, cudaStream_t st) {
+                        unsigned flags, cudaStream_t st, const GroupedFusedHost* fu) {
     GrpPlan pl;
     if (count <= 0) return QGTC_ERR_INVALID_ARG;
-    if (!grp_supports(N, bit1, bit2, epi) || !plan_for(N, bit1, bit2, pl)) return QGTC_ERR_UNSUPPORTED;
+    if (!grp_supports(N, bit1, bit2, epi)) return QGTC_ERR_UNSUPPORTED;
+    if (fu) {
+        if (epi != kEpiBitsRow || !grp_supports_fused(N, bit1, bit2, fu->N2, fu->bit_w, fu->epi2)) return QGTC_ERR_UNSUPPORTED;
+        if (!plan_for(N, bit1, bit2, pl, fu->N2, fu->bit_w)) return QGTC_ERR_UNSUPPORTED;
+    } else if (!plan_for(N, bit1, bit2, pl)) {
+        return QGTC_ERR_UNSUPPORTED;
+    }
     for (int i = 0; i < count; ++i)    // a single problem larger than one launch can hold: not this engine
         if ((long long)((p8(probs[i].M) + 127) / 128) > (long long)kNumSMs * kMaxUnitsPerCta) return QGTC_ERR_UNSUPPORTED;
     unsigned int* ef = tc05_error_flag_device();
@@ -775,7 +978,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             const long long u = (p8(h.M) + 127) / 128;
             if (n > 0 && units + u > (long long)kNumSMs * kMaxUnitsPerCta) break;
             GrpProblem& p = T.p[n];
-            p.x1 = h.x1; p.x2 = h.x2; p.out = h.out;
+            p.x1 = h.x1; p.x2 = h.x2; p.out = h.out; p.out2 = fu ? h.out2 : nullptr; p.pad_ = 0;
             p.bitmap = bit1 == 1 ? h.bitmap : nullptr;
             if (p.bitmap) any_bitmap = 1;
             p.x1_words = h.x1_words; p.x2_words = h.x2_words;
@@ -807,6 +1010,11 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         T.a_slot_bytes = pl.a_slot; T.b_slot_bytes = pl.b_slot; T.b_stage_bytes = pl.b_stage; T.b_ring = pl.b_ring;
         T.off_bstage = pl.off_bstage; T.off_bring = pl.off_bring; T.off_bars = pl.off_bars; T.off_flags = pl.off_flags; T.off_misc = pl.off_misc;
         T.off_units = pl.off_units;
+        T.fused = fu ? 1 : 0;
+        T.N2 = fu ? fu->N2 : 0; T.NP2 = pl.NP2; T.bit_w = fu ? fu->bit_w : 0; T.out_bit2 = fu ? fu->out_bit2 : 0;
+        T.epi2 = fu ? fu->epi2 : 0; T.pad128_2 = fu ? fu->pad128_2 : 0; T.write_out1 = fu ? fu->write_out1 : 0;
+        T.a2_col = pl.a2_col; T.d2_col = pl.d2_col; T.off_b2 = pl.off_b2;
+        T.w2 = fu ? fu->w : nullptr; T.w2_words = fu ? fu->w_words : 0;
         T.cps_inv = pl.cps == 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)pl.cps - 1ull) / (unsigned long long)pl.cps);
         T.flags = flags;
         T.error_flag = ef;

@@ -293,6 +293,80 @@ std::vector<torch::Tensor> bitMM2Int_grouped(std::vector<torch::Tensor> X1s, std
     return grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, 1, QGTC_GROUP_FLOAT, pad_128, tile_maps, (unsigned)static_operands << 3, "bitMM2Int_grouped");
 }
 
+// Fused aggregation + update for all problems of a list in one launch (qgtc_bitmm_grouped_fused): returns the second op's
+// outputs.  Falls back to two grouped launches when the shapes do not fit the fused kernel (identical results).
+std::vector<torch::Tensor> fused_impl(const std::vector<torch::Tensor>& X1s, const std::vector<torch::Tensor>& X2s, const std::vector<int64_t>& Ms,
+                                      const std::vector<int64_t>& Ks, int N, int bit1, int bit2, int out_bit, const torch::Tensor& W, int N2, int bit_w,
+                                      int out_bit2, bool float_out, bool pad_128, const std::vector<torch::Tensor>& tile_maps, unsigned static_flags) {
+    const char* op = "bitMM2Bit_grouped_fused";
+    const size_t count = X1s.size();
+    TORCH_CHECK(count > 0 && X2s.size() == count && Ms.size() == count && Ks.size() == count, op, ": operand lists must be non-empty and of equal length");
+    TORCH_CHECK(tile_maps.empty() || tile_maps.size() == count, op, ": tile_maps must be empty or hold one bitmap per problem");
+    CHECK_INPUT(W);
+    const c10::cuda::CUDAGuard guard(X1s[0].device());
+    auto w = packed_input(W, "bit_W");
+    std::vector<torch::Tensor> keep;
+    std::vector<qgtc_group_problem> probs(count);
+    std::vector<void*> out2_ptr(count);
+    std::vector<size_t> out2_size(count);
+    std::vector<int64_t> offs(count), sizes(count), rows(count), cols(count);
+    int64_t total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        TORCH_CHECK(Ms[i] > 0 && Ks[i] > 0, "dimensions must be positive");
+        if (float_out) { rows[i] = Ms[i]; cols[i] = N2; }
+        else qgtc_packed_shape(QGTC_LAYOUT_ROW, out_bit2, (int)Ms[i], N2, &rows[i], &cols[i]);
+        sizes[i] = rows[i] * cols[i];
+        offs[i] = total;
+        total += (sizes[i] + 3) & ~(int64_t)3;
+    }
+    auto flat = torch::empty({total}, X1s[0].options().dtype(float_out ? torch::kFloat32 : torch::kInt32));
+    std::vector<torch::Tensor> outs(count);
+    for (size_t i = 0; i < count; ++i) {
+        CHECK_INPUT(X1s[i]);
+        CHECK_INPUT(X2s[i]);
+        keep.push_back(packed_input(X1s[i], "bit_X1"));
+        keep.push_back(packed_input(X2s[i], "bit_X2"));
+        const torch::Tensor &a = keep[keep.size() - 2], &b = keep[keep.size() - 1];
+        outs[i] = flat.narrow(0, offs[i], sizes[i]).view({rows[i], cols[i]});
+        qgtc_group_problem& p = probs[i];
+        p.x1_dev = a.data_ptr<int32_t>();
+        p.x1_words = (size_t)a.numel();
+        p.x2_dev = b.data_ptr<int32_t>();
+        p.x2_words = (size_t)b.numel();
+        p.out_dev = nullptr;
+        p.out_size = 0;
+        p.tile_bitmap_dev = nullptr;
+        if (!tile_maps.empty() && tile_maps[i].defined() && tile_maps[i].numel() > 0) {
+            TORCH_CHECK(tile_maps[i].is_cuda() && tile_maps[i].scalar_type() == torch::kInt32 && tile_maps[i].is_contiguous(), "tile_map must be a contiguous int32 CUDA tensor");
+            TORCH_CHECK((size_t)tile_maps[i].numel() >= qgtc_tile_bitmap_words((int)Ms[i], (int)Ks[i], 1), "tile_map too small for its problem");
+            p.tile_bitmap_dev = reinterpret_cast<const uint32_t*>(tile_maps[i].data_ptr<int32_t>());
+        }
+        p.M = (int32_t)Ms[i];
+        p.K = (int32_t)Ks[i];
+        out2_ptr[i] = outs[i].data_ptr();
+        out2_size[i] = (size_t)sizes[i];
+    }
+    const qgtc_fused_update upd{w.data_ptr<int32_t>(), (size_t)w.numel(), N2, bit_w, out_bit2, float_out ? QGTC_GROUP_FLOAT : QGTC_GROUP_BITS_ROW, pad_128 ? 1 : 0};
+    const unsigned fl = flags_from_env() | (static_flags & (QGTC_FLAG_X1_STATIC | QGTC_FLAG_X2_STATIC));
+    const int rc = qgtc_bitmm_grouped_fused(probs.data(), (int)count, N, bit1, bit2, out_bit, &upd, out2_ptr.data(), out2_size.data(), 0, engine_from_env(), fl,
+                                            current_stream());
+    if (rc == QGTC_ERR_UNSUPPORTED) {      // shapes outside the fused kernel: the same two ops, one grouped launch each
+        auto mid = grouped_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, QGTC_GROUP_BITS_ROW, true, tile_maps, static_flags, op);
+        std::vector<torch::Tensor> Ws(count, W);
+        std::vector<int64_t> K2(count, (int64_t)N);
+        return grouped_impl(mid, Ws, Ms, K2, N2, out_bit, bit_w, float_out ? 1 : out_bit2, float_out ? QGTC_GROUP_FLOAT : QGTC_GROUP_BITS_ROW, pad_128, {},
+                            QGTC_FLAG_X2_STATIC, op);
+    }
+    check_status(rc, op);
+    return outs;
+}
+
+std::vector<torch::Tensor> bitMM2Bit_grouped_fused(std::vector<torch::Tensor> X1s, std::vector<torch::Tensor> X2s, std::vector<int64_t> Ms, std::vector<int64_t> Ks,
+                                                   int N, int bit1, int bit2, int out_bit, torch::Tensor W, int N2, int bit_w, int out_bit2, bool float_out,
+                                                   bool pad_128, std::vector<torch::Tensor> tile_maps, int static_operands) {
+    return fused_impl(X1s, X2s, Ms, Ks, N, bit1, bit2, out_bit, W, N2, bit_w, out_bit2, float_out, pad_128, tile_maps, (unsigned)static_operands << 3);
+}
+
 torch::Tensor tile_bitmap(torch::Tensor bit_X1, const int M, const int K) {
     CHECK_INPUT(bit_X1);
     const c10::cuda::CUDAGuard guard(bit_X1.device());
@@ -340,6 +414,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"));
     m.def("bitMM2Int_grouped", &bitMM2Int_grouped, "one launch: bitMM2Int of every problem of a list (same N and bit widths)", py::arg("X1s"),
           py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("pad_128"),
+          py::arg("tile_maps") = std::vector<torch::Tensor>(), py::arg("static_operands") = 0);
+    m.def("bitMM2Bit_grouped_fused", &bitMM2Bit_grouped_fused,
+          "one launch: out2[i] = op2(bitMM2Bit(X1s[i], X2s[i]), W) with op2 = bitMM2Bit (float_out = False) or bitMM2Int (True) and one shared W",
+          py::arg("X1s"), py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"), py::arg("W"),
+          py::arg("N2"), py::arg("bit_w"), py::arg("out_bit2"), py::arg("float_out") = false, py::arg("pad_128") = false,
           py::arg("tile_maps") = std::vector<torch::Tensor>(), py::arg("static_operands") = 0);
     m.def("tile_bitmap", &tile_bitmap, "non-zero 128 x 128-bit tile bitmap of a packed 1-bit adjacency (zero-tile jumping)");
     m.def("edges2bit", &edges2bit, "packed 1-bit adjacency R(1,H,W) from int32 edge endpoints (no dense fp32 intermediate)");

@@ -47,6 +47,7 @@ def build_parser():
     p.add_argument("--streams", type=int, default=1, help="run independent batches on this many CUDA streams (they share nothing)")
     p.add_argument("--grouped", action="store_true",
                    help="issue the epoch op-major: ONE grouped launch per op over all of this rank's batches (6 launches per epoch)")
+    p.add_argument("--no-fuse", action="store_true", help="--grouped: one launch per op (six per epoch) instead of fusing each update GEMM into the aggregation before it")
     p.add_argument("--tile-bitmap", choices=["auto", "on", "off"], default="auto",
                    help="--grouped: pass the batches' tile bitmaps (zero-tile jumping); auto = when under half of the tiles are non-zero")
     p.add_argument("--min-region-ms", type=float, default=0.0, help="--cuda-graph: replay enough epochs for a timed region of at least this many ms")
@@ -80,7 +81,7 @@ def gin_forward(QGTC, bit_A, bit_X, W, n, D, bw):
     return QGTC.bitMM2Int(o, bit_W3, n, h2, out, bw, bw, False)
 
 
-def grouped_forward(QGTC, run_gin, A, X, tile_maps, W, ns, D, bw):
+def grouped_forward(QGTC, run_gin, A, X, tile_maps, W, ns, D, bw, fused=True):
     """The same six ops for ALL batches, op-major: op i of every batch is one grouped launch (QGTC.bitMM2*_grouped), so an
     epoch is six kernels instead of six per batch.  Batches are independent and every op is the reference's op on the same
     raw memory, so each batch's result is bit-identical to gcn_forward / gin_forward (main_qgtc.py:128-154)."""
@@ -90,6 +91,17 @@ def grouped_forward(QGTC, run_gin, A, X, tile_maps, W, ns, D, bw):
     # static_operands: the adjacency (X1 of the aggregations, with its tile bitmap) and the weights (X2 of the updates) are not
     # produced by the previous op, so the kernel may load them while that op is still draining (programmatic dependent launch)
     SA, SW = 1, 2
+    if fused:
+        # every update GEMM (o.W: K = hidden <= 64) rides in the epilogue of the aggregation before it (QGTC.bitMM2Bit_grouped_fused):
+        # the requantized tile goes straight back into tensor memory as the second GEMM's A operand.  GCN: 4 launches, GIN: 3.
+        if run_gin:
+            o = QGTC.bitMM2Bit_grouped_fused(A, X, ns, ns, D, 1, bw, bw, bit_W1, h1, bw, bw, False, False, tile_maps, SA | SW)
+            o = QGTC.bitMM2Bit_grouped_fused(A, o, ns, ns, h1, 1, bw, bw, bit_W2, h2, bw, bw, False, False, tile_maps, SA)
+            return QGTC.bitMM2Bit_grouped_fused(A, o, ns, ns, h2, 1, bw, bw, bit_W3, out, bw, bw, True, False, tile_maps, SA)
+        o = QGTC.bitMM2Bit_grouped(X, W1, ns, [D] * B, h1, bw, bw, bw, [], SA | SW)
+        o = QGTC.bitMM2Bit_grouped_fused(A, o, ns, ns, h1, 1, bw, bw, bit_W2, h2, bw, bw, False, False, tile_maps, SA)
+        o = QGTC.bitMM2Bit_grouped_fused(A, o, ns, ns, h2, 1, bw, bw, bit_W3, out, bw, bw, False, False, tile_maps, SA)
+        return QGTC.bitMM2Int_grouped(A, o, ns, ns, h2, 1, bw, False, tile_maps, SA)
     if run_gin:
         o = QGTC.bitMM2Bit_grouped(A, X, ns, ns, D, 1, bw, bw, tile_maps, SA | SW)
         o = QGTC.bitMM2Bit_grouped(o, W1, ns, [D] * B, h1, bw, bw, bw, [], SW)
@@ -195,7 +207,7 @@ def run(args, graph=None, quiet=False, ops=None):
         gmaps = list(it.tile_maps) if use_maps else []
 
         def one_epoch():  # noqa: F811  (op-major: six grouped launches)
-            res = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw)
+            res = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw, fused=not getattr(args, "no_fuse", False))
             return res[-1]
 
     if args.zerotile_jump:
@@ -267,7 +279,7 @@ def run(args, graph=None, quiet=False, ops=None):
     if getattr(args, "gather_logits", False):
         # one more (untimed) forward that keeps every batch's logits, then the only data collective of the path
         if grouped:
-            mine = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw)
+            mine = grouped_forward(QGTC, args.run_GIN, gA, gX, gmaps, W, gns, feat_size, bw, fused=not getattr(args, "no_fuse", False))
         else:
             mine = [fwd(QGTC, c.bit_A, c.bit_X, W, p_[0], p_[3], bw) for c, p_ in it]
         full = C.gather_logits(list(mine), list(it.batch_ids), counts, world)

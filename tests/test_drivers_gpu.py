@@ -98,8 +98,9 @@ def test_grouped_forward_equals_per_batch_forward(run_gin):
         want = [fwd(QGTC, c.bit_A, c.bit_X, W, p[0], D, bits) for c, p in it]
         A, X, ns = [c.bit_A for c in it.cTensor_li], [c.bit_X for c in it.cTensor_li], [p[0] for p in it.cluster_param_li]
         for maps in ([], list(it.tile_maps)):
-            got = drv.grouped_forward(QGTC, run_gin, A, X, maps, W, ns, D, bits)
-            assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+            for fused in (False, True):
+                got = drv.grouped_forward(QGTC, run_gin, A, X, maps, W, ns, D, bits, fused=fused)
+                assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want)), (bits, fused, bool(maps))
         assert 0.0 < it.nonzero_tile_fraction() <= 1.0
 
 

@@ -232,6 +232,63 @@ def test_op_major_chains_match_oracle(capi, coracle, kind, D, h, C, b):
         assert np.array_equal(v["o"].cpu().numpy(), w), i
 
 
+@pytest.mark.parametrize("N,N2,b,kind2,pad", [(16, 16, 2, 0, False), (16, 121, 2, 0, False), (64, 64, 2, 0, False), (29, 64, 2, 0, False), (64, 2, 2, 1, False),
+                                                (16, 16, 1, 0, False), (16, 40, 4, 0, False), (16, 16, 8, 0, False), (48, 128, 3, 1, True), (33, 7, 5, 1, False)])
+def test_fused_aggregation_update_equals_two_ops(capi, coracle, N, N2, b, kind2, pad):
+    """qgtc_bitmm_grouped_fused: out2 = op2(bitMM2Bit(A, X), W) in one launch == the two ops of main_qgtc.py:148+150 etc. through the
+    oracle, for several batches of different size (with tile bitmaps, with and without writing the first op's own result)."""
+    rng = np.random.default_rng(N * 1000 + N2 * 10 + b)
+    ns = [759, 300, 1283, 70, 128, 1]
+    W = coracle.val2bit(rand_features(rng, (N, N2), b), b, True, kind2 == 1 and not pad)
+    x1s, x2s, want1, want2 = [], [], [], []
+    for n in ns:
+        A = rand_adj(rng, n, n, 0.03, zero_blocks=True)
+        X = rand_features(rng, (n, N), b)
+        ba, bx = coracle.val2bit(A, 1, False, False), coracle.val2bit(X, b, True, False)
+        o1 = coracle.bitMM2Bit(ba, bx, n, n, N, 1, b, b)
+        x1s.append(dev_words(ba)); x2s.append(dev_words(bx)); want1.append(o1)
+        want2.append(coracle.bitMM2Int(o1, W, n, N, N2, b, b, pad) if kind2 == 1 else coracle.bitMM2Bit(o1, W, n, N, N2, b, b, b))
+    dW = dev_words(W)
+    maps = [capi.tile_bitmap(a, n, n).view(-1) for a, n in zip(x1s, ns)]
+    for tm, w1 in ((None, False), (maps, True)):
+        outs2, outs1 = capi.bitmm_grouped_fused(x1s, x2s, ns, ns, N, 1, b, b, dW, N2, b, b, kind2=kind2, pad_128=pad, tile_maps=tm, write_out1=w1,
+                                                engine=capi.ENGINE_GROUPED)
+        for i in range(len(ns)):
+            g = outs2[i].cpu().numpy()
+            assert np.array_equal(g.view(np.uint32) if g.dtype == np.int32 else g, want2[i]), (i, ns[i], w1)
+            if w1:
+                assert np.array_equal(host_u32(outs1[i]), want1[i]), (i, ns[i])
+
+
+def test_fused_many_units_per_cta(capi, coracle):
+    """Hundreds of units per launch: every CTA runs several fused units back to back (A2 / D2 re-use across units)."""
+    N, N2, b = 16, 16, 2
+    rng = np.random.default_rng(5)
+    W = coracle.val2bit(rand_features(rng, (N, N2), b), b, True, False)
+    pool = []
+    for n in (759, 515, 300, 129):
+        ba = coracle.val2bit(rand_adj(rng, n, n, 0.02), 1, False, False)
+        bx = coracle.val2bit(rand_features(rng, (n, N), b), b, True, False)
+        o1 = coracle.bitMM2Bit(ba, bx, n, n, N, 1, b, b)
+        pool.append((n, dev_words(ba), dev_words(bx), dev_words(coracle.bitMM2Bit(o1, W, n, N, N2, b, b, b))))
+    picks = [pool[int(i)] for i in rng.integers(0, len(pool), size=150)]
+    ns = [p[0] for p in picks]
+    for _ in range(2):
+        outs2, _ = capi.bitmm_grouped_fused([p[1] for p in picks], [p[2] for p in picks], ns, ns, N, 1, b, b, dev_words(W), N2, b, b,
+                                            engine=capi.ENGINE_GROUPED)
+        torch.cuda.synchronize()
+        bad = [i for i, (o, p) in enumerate(zip(outs2, picks)) if not torch.equal(o, p[3])]
+        assert not bad, bad[:10]
+
+
+def test_fused_refuses_shapes_outside_the_kernel(capi):
+    a = torch.zeros((8, 4), dtype=torch.int32, device="cuda")
+    x = torch.zeros((4, 128), dtype=torch.int32, device="cuda")
+    w = torch.zeros((4, 128), dtype=torch.int32, device="cuda")
+    with pytest.raises(capi.QgtcError, match="unsupported"):
+        capi.bitmm_grouped_fused([a], [x], [8], [8], 100, 1, 1, 1, w, 8, 1, 1)       # N = 100 > 64: the caller issues two launches
+
+
 def test_grouped_rejects_bad_arguments(capi):
     a = torch.zeros((8, 4), dtype=torch.int32, device="cuda")
     x = torch.zeros((4, 128), dtype=torch.int32, device="cuda")
