@@ -710,7 +710,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                         for (int w = (NP + 31) / 32; w < wpr; ++w) out[(unsigned long long)p * opt_offset + (unsigned long long)m * wpr + w] = 0u;
                     }
                 }
-                // ---- A2 operand: byte i of register 8 s + c = value of column 32 s + c + 8 i (the K permutation W's image uses)
+                // ---- A2 operand in the K permutation W's image uses: byte i of register 8 s + c <-> BIT c + 8 i of packed word s, and
+                // the packed words are MSB-first (column e of a 32-group is bit 31 - e): byte i of register 8 s + c = value of
+                // column 32 s + 31 - c - 8 i, i.e. the natural gather below with the register order and the bytes reversed.
                 uint32_t a2[16];
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 #pragma unroll
                         for (int tt = 0; tt < 4; ++tt) {
                             const uint32_t sel = (uint32_t)(tt | ((4 + tt) << 4));
-                            a2[8 * s2 + 4 * cq + tt] = __byte_perm(__byte_perm(r0, r1, sel), __byte_perm(r2, r3, sel), 0x5410u);
+                            a2[8 * s2 + 7 - (4 * cq + tt)] = __byte_perm(__byte_perm(r0, r1, sel), __byte_perm(r2, r3, sel), 0x0145u);
                         }
                     }
                 }
