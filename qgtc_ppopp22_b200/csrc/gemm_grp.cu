@@ -213,6 +213,49 @@ __device__ __forceinline__ uint32_t assemble_planes_rt(int nb, const unsigned ch
     return any;
 }
 
+// Half of a chunk (words 2 h and 2 h + 1 of every plane -> 16 registers = k groups 4 h .. 4 h + 3): when an item has at most 64
+// (chunk, column) tasks, two converter threads share each task so that all four converter warps work on every item.
+template <int NB, bool SCALED>
+__device__ __forceinline__ void assemble_half(const unsigned char* src, int stride, int h, uint32_t (&r)[16]) {
+#pragma unroll
+    for (int p = 0; p < NB; ++p) {
+        const uint4 pv = *reinterpret_cast<const uint4*>(src + p * stride);
+        const uint32_t w[2] = {h ? pv.z : pv.x, h ? pv.w : pv.y};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int to = p + (SCALED ? 3 - (c & 3) : 0);
+                const uint32_t sh = c >= to ? (w[ks] >> (c - to)) : (w[ks] << (to - c));
+                const uint32_t v = sh & (0x01010101u << to);
+                r[ks * 8 + c] = p == 0 ? v : (r[ks * 8 + c] | v);
+            }
+        }
+    }
+}
+template <bool SCALED>
+__device__ __forceinline__ void assemble_half_rt(int nb, const unsigned char* src, int stride, int h, uint32_t (&r)[16]) {
+    switch (nb) {
+        case 1: assemble_half<1, SCALED>(src, stride, h, r); return;
+        case 2: assemble_half<2, SCALED>(src, stride, h, r); return;
+        case 4: assemble_half<4, SCALED>(src, stride, h, r); return;
+        case 8: if (!SCALED) { assemble_half<8, false>(src, stride, h, r); return; } break;
+        default: break;
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r[e] = 0u;
+#pragma unroll 1
+    for (int p = 0; p < nb; ++p) {
+        const uint4 pv = *reinterpret_cast<const uint4*>(src + p * stride);
+        const uint32_t w[2] = {h ? pv.z : pv.x, h ? pv.w : pv.y};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) r[ks * 8 + c] |= ((w[ks] >> c) & 0x01010101u) << (p + (SCALED ? 3 - (c & 3) : 0));
+        }
+    }
+}
+
 // fast path first: a plain try_wait (already-complete phases return at once), then the bounded suspending wait
 __device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity, unsigned int* ef, int where) {
     if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity, ef, where, true);
@@ -455,10 +498,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const int t = threadIdx.x - kConvWarp0 * 32;
         const int p8n = p8(T.N);
         const int pn = T.pad128 ? p128(T.N) : p8n;                     // columns per plane of X2: kernel.h:266 / :836
+        // At most 64 tasks per item (cps * NP <= 64, e.g. N = 16): two threads share a task, each converting one half of the chunk
+        // (threads 0-63: words 0-1, threads 64-127: words 2-3), so that all four converter warps work on every item.
+        const bool split = CPS * NP <= 64;
+        const int half = split ? (t >> 6) : 0;
         int tj[kMaxTasks], tn_[kMaxTasks];                             // this thread's tasks: chunk within the item, column
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
-            const int task = t + i * kConvThreads;
+            const int task = split ? ((t & 63) + i * 64 * 1024) : (t + i * kConvThreads);   // split: one task per thread (the second is out of range)
             tj[i] = task / NP;
             tn_[i] = task - tj[i] * NP;
         }
@@ -557,6 +604,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < kMaxTasks; ++i) {
                     if (tj[i] >= nch) continue;
+                    if (split) {
+                        if (i == 0) {
+                            uint32_t o[16];
+                            if (A1 && mode2) assemble_half_rt<true>(T.bit2, src, kConvThreads * 16, half, o);
+                            else assemble_half_rt<false>(T.bit2, src, kConvThreads * 16, half, o);
+                            unsigned char* dsth = stage + (size_t)tj[0] * NP * 128 + (size_t)(tn_[0] >> 3) * 128 + (tn_[0] & 7) * 16 + (size_t)(4 * half) * (NP / 8) * 128;
+#pragma unroll
+                            for (int kg = 0; kg < 4; ++kg)
+                                *reinterpret_cast<uint4*>(dsth + (size_t)kg * (NP / 8) * 128) = make_uint4(o[4 * kg], o[4 * kg + 1], o[4 * kg + 2], o[4 * kg + 3]);
+                        }
+                        continue;
+                    }
                     uint32_t o[32];
                     if (A1 && mode2) assemble_planes_rt<true>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
                     else assemble_planes_rt<false>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
