@@ -165,3 +165,25 @@ def test_arxiv_shaped_chain_matches_oracle(coracle, bits):
     t = o.bitMM2Bit(t, oW[2], n, h, ncls, b, b, b)
     want = o.bitMM2Int(bA, t, n, n, h, 1, b, False)
     assert np.array_equal(got, want)
+
+
+def test_extension_fused_op_falls_back_outside_the_fused_kernel(coracle):
+    """QGTC.bitMM2Bit_grouped_fused with N = 100 (> 64: not the fused kernel) issues the two grouped launches itself: same results."""
+    import qgtc_ppopp22_b200
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    rng = np.random.default_rng(4)
+    b, N, N2 = 2, 100, 24
+    ns = [300, 129]
+    W = torch.from_numpy(coracle.val2bit(rng.integers(0, 4, (N, N2)).astype(np.float32), b, True, False).view(np.int32)).cuda()
+    A, X, want = [], [], []
+    for n in ns:
+        a = coracle.val2bit((rng.random((n, n)) < 0.05).astype(np.float32), 1, False, False)
+        x = coracle.val2bit(rng.integers(0, 4, (n, N)).astype(np.float32), b, True, False)
+        o1 = coracle.bitMM2Bit(a, x, n, n, N, 1, b, b)
+        want.append(coracle.bitMM2Bit(o1, W.cpu().numpy().view(np.uint32), n, N, N2, b, b, b))
+        A.append(torch.from_numpy(a.view(np.int32)).cuda())
+        X.append(torch.from_numpy(x.view(np.int32)).cuda())
+    for NN, (AA, XX, ww) in ((N, (A, X, want)),):
+        got = QGTC.bitMM2Bit_grouped_fused(AA, XX, ns, ns, NN, 1, b, b, W, N2, b, b)
+        for g, w in zip(got, ww):
+            assert np.array_equal(g.cpu().numpy().view(np.uint32), w)
