@@ -82,7 +82,6 @@ struct Tc05Args {
     const uint32_t* bitmap;         // optional tile bitmap (qgtc_tile_bitmap): [count][mtiles][bmw] words of chunk bits
     int bmw;                        // bitmap words per tile = ceil(gdk / 32)
     int rslots;                     // raw adjacency ring slots in use (<= kRawSlots)
-    int ss;                         // 1: the LAST stage's expanded adjacency lives in shared memory (SS-form MMA) instead of TMEM: a fourth stage for the u8 path
     unsigned int cps_inv;           // ceil(2^32 / cps): stage of a chunk by one multiply
     int amode;                      // 3 = 4-bit operand path (kind::mxf4, adjacency bit -> E2M1 nibble, features as E2M1); else adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
@@ -100,9 +99,9 @@ constexpr int kTraceItems = 512;    // per role: [item][8] timestamps
 // PTX wrappers and the epilogue helpers live in tc05_common.cuh (shared with gemm_grp.cu)
 struct SmemLayout {
     // offsets in bytes from the 1024-byte aligned base
-    int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total, a_ss0;
+    int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, int pair = 0, int rslots = kRawSlots, int f4 = 0, int ss = 0) {
+__host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, int pair = 0, int rslots = kRawSlots, int f4 = 0) {
     SmemLayout L;
     L.raw0 = 0;
     L.raw_slot_bytes = 128 * 16 * cps;                 // 2/4/8 KB, keeps every slot 1024-byte aligned for the swizzle
@@ -110,8 +109,7 @@ __host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, i
     L.raw_slot_bytes = (L.raw_slot_bytes + 1023) & ~1023;
     L.b_stage0 = L.raw0 + rslots * L.raw_slot_bytes;
     L.b_stage_bytes = cps * NP * ((pair || f4) ? 64 : 128);    // pair mode: each CTA holds half of the feature columns; 4-bit path: half the bytes
-    L.a_ss0 = L.b_stage0 + stages * L.b_stage_bytes;  // expanded adjacency of the shared-memory stage: cps chunks x 128 rows x 128 B, K-major core matrices
-    L.bars = L.a_ss0 + (ss ? cps * 128 * 128 : 0);
+    L.bars = L.b_stage0 + stages * L.b_stage_bytes;
     L.flags = L.bars + (3 * kMaxStages + 2 * kRawSlots + 6) * 8;
     L.misc = L.flags + kMaxStages * 32;                // flags: [stage][chunk <= 8][lane quarter]
     L.total = L.misc + 32;
@@ -310,7 +308,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
     constexpr int kCh = F4 ? kMaxCps4 : kMaxCps;          // chunks per item, compile-time bound
     constexpr int kChunkCols = F4 ? 16 : 32;              // TMEM columns of one expanded chunk
-    const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0, T.rslots, F4 ? 1 : 0, T.ss);
+    const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0, T.rslots, F4 ? 1 : 0);
     const int rank = PAIR ? (int)cluster_ctarank() : 0;            // 0 = leader (issues the MMAs)
     const int group_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int ngroups = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -491,19 +489,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // other three lane quarters are zero too.
             unsigned nzmask = 0;
             const uint32_t st_s = st_addr + (uint32_t)(s * stage_cols);
-            // shared-memory stage (T.ss, last stage): the 128 bytes of this row and chunk go to the canonical K-major core-matrix
-            // layout [k group (8)][row block (16)][8 rows][16 B] (K-direction stride 2048 B, row-block stride 128 B) instead of TMEM
-            const bool ss_item = !F4 && !PAIR && T.ss && s == S - 1;
-            unsigned char* ss_row = smem_raw + L.a_ss0 + (size_t)(row >> 3) * 128 + (row & 7) * 16;
-            auto store_chunk = [&](int j, const uint32_t (&r)[32]) {
-                if (ss_item) {
-#pragma unroll
-                    for (int kg = 0; kg < 8; ++kg)
-                        *reinterpret_cast<uint4*>(ss_row + (size_t)(c0 + j) * 16384 + (size_t)kg * 2048) = make_uint4(r[4 * kg], r[4 * kg + 1], r[4 * kg + 2], r[4 * kg + 3]);
-                } else {
-                    tmem_st32(st_s + (uint32_t)(32 * j), r);
-                }
-            };
             if (F4) {
                 {
                     uint32_t r[16];
@@ -531,7 +516,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                     mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
                     tc_fence_after();
                     if (tr) QGTC_TRACE(trole, k, 3);
-                    if (!dbg_no_st) store_chunk(0, r);
+                    if (!dbg_no_st) tmem_st32(st_s, r);
                     else if (r[5] == 0xdeadbeefu) flags[255] = 1;  // keep the expansion alive
                 }
 #pragma unroll
@@ -540,7 +525,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         uint32_t r[32];
                         if (is_nonzero(v[j])) nzmask |= 1u << j;
                         expand(v[j], r);
-                        if (!dbg_no_st) store_chunk(j, r);
+                        if (!dbg_no_st) tmem_st32(st_s + (uint32_t)(32 * j), r);
                         else if (r[5] == 0xdeadbeefu) flags[255] = 1;
                     }
                 }
@@ -550,8 +535,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             if (lane == 0) mbar_arrive(&raw_empty[slot]);
             if (lane < WCH) my_flags[s * 32 + lane * 4] = (unsigned char)((nzmask >> lane) & 1u);
             if (tr) QGTC_TRACE(trole, k, 4);
-            if (ss_item) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> the MMA's async-proxy reads
-            else if (!dbg_no_st) tmem_wait_st();
+            if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
             if (tr) QGTC_TRACE(trole, k, 5);
             __syncwarp();   // every lane's tcgen05.st has completed, the flags are written
@@ -678,9 +662,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const uint32_t stage_lo = (uint32_t)L.b_stage_bytes >> 4;
             const uint32_t chunk_lo = ((uint32_t)NP * ((PAIR || F4) ? 64u : 128u)) >> 4;
             const uint32_t kstep_lo = (2u * lbo) >> 4;   // one MMA's K: two core matrices (u8: 2 x 16 elements, 4-bit: 2 x 32)
-            // shared-memory A stage (T.ss): K-major, no swizzle, K-direction stride 2048 B, row-block stride 128 B; 16 KB per chunk, 4 KB per MMA
-            const uint64_t adesc0 = make_smem_desc(smem_u32(smem_raw + L.a_ss0), 2048u, 128u);
-            const uint32_t adesc_hi = (uint32_t)(adesc0 >> 32), alo0 = (uint32_t)adesc0;
             int s = 0, buf = 0, item = 0, owner = 0;   // owner = item % T.ni
             uint32_t use = 0, duse = 0;
             auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
@@ -731,8 +712,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                                             const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
                                             const uint32_t d_use = (dbg_alt_d && (ks & 1)) ? (d_tmem ^ (uint32_t)NP) : d_tmem;
                                             if (PAIR) mma_i8_ts_pair(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
-                                            else if (T.ss && s == S - 1)
-                                                mma_i8_ss(d_use, ((uint64_t)adesc_hi << 32) | (uint64_t)(alo0 + (uint32_t)j * (16384u >> 4) + (uint32_t)ks * (4096u >> 4)), desc, idesc, 1u);
                                             else mma_i8_ts(d_use, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
                                         }
                                     }
@@ -975,20 +954,10 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     int stages = f4 ? (kTmemCols - T.dbufs * T.NP - kSfCols) / (T.cps * 16) : (kTmemCols - T.dbufs * T.NP) / (T.cps * 32);
     if (stages > kMaxStages) stages = kMaxStages;
     T.rslots = f4 ? 6 : kRawSlots;      // 4-bit path: raw slots are up to 14 KB
-    // Optional fourth stage for the u8 path (QGTC_TC05_SS=1): three stages in tensor memory plus one whose expanded adjacency lives
-    // in shared memory (SS-form MMA); the raw ring shrinks to four slots to make room (64 KB for a 4-chunk stage).
-    static const bool ss_env = [] { const char* e = getenv("QGTC_TC05_SS"); return e && e[0] == '1'; }();
-    T.ss = 0;
-    if (ss_env && !f4 && !pair && stages == 3 && T.cps == 4 && (a.flags & 0x6F0000u) == 0 &&
-        smem_layout(T.NP, 4, T.cps, 0, 4, 0, 1).total + 1024 <= 227 * 1024) {
-        T.ss = 1;
-        stages = 4;
-        T.rslots = 4;
-    }
     // (Converting the features inside this kernel, by an expander group without items, was built and measured on
     // B200 -- 4096 x 4096 x 64, 96 graphs: +17 us at 1 bit, +83 us at 8 bits per launch against 8-17 us for the
     // separate prep kernel: the GEMM warps have no issue slots to spare.  Removed)
-    while (!T.ss && stages > 2 && smem_layout(T.NP, stages, T.cps, pair, T.rslots, f4).total > 200 * 1024) --stages;
+    while (stages > 2 && smem_layout(T.NP, stages, T.cps, pair, T.rslots, f4).total > 200 * 1024) --stages;
     if (stages < 2) return QGTC_ERR_UNSUPPORTED;
     T.stages = stages;
     T.mtiles = (p8(a.M) + 127) / 128;
@@ -1094,7 +1063,7 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     }
 
     if (rc == QGTC_OK) {
-        const int smem = smem_layout(T.NP, T.stages, T.cps, pair, T.rslots, f4, T.ss).total + 1024;
+        const int smem = smem_layout(T.NP, T.stages, T.cps, pair, T.rslots, f4).total + 1024;
         const int groups = pair ? (T.units < kNumSMs / 2 ? T.units : kNumSMs / 2) : (T.units < kNumSMs ? T.units : kNumSMs);
         auto launch = [&](auto kfn) -> int {
             cudaError_t e2 = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
