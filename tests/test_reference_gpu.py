@@ -53,3 +53,41 @@ def test_committed_golden_vectors_match_this_box(ref, capfd):
         for k in g0.files:
             assert mg.same(g0[k], g1[k]), (name, k)
     capfd.readouterr()
+
+
+@pytest.mark.parametrize("run_gin", [False, True])
+@pytest.mark.parametrize("bits", [1, 2])
+def test_reference_chain_vs_grouped_fused_forward(ref, capfd, run_gin, bits):
+    """The whole six-op forward of main_qgtc.py:128-154 run batch by batch through the REFERENCE's own kernels (same sources,
+    logical warp index) against this repo's op-major path: one grouped launch per op with every update GEMM fused into the
+    aggregation before it (4 launches for GCN, 3 for GIN).  Shapes inside the reference's well-defined domain (C = 121 -> P8 == P128;
+    ppi-sized and smaller batches)."""
+    import qgtc_ppopp22_b200
+    from qgtc_ppopp22_b200 import main_qgtc as drv
+    QGTC = qgtc_ppopp22_b200.load_extension()
+    torch.manual_seed(3)
+    D, h, C = 50, 16, 128 if run_gin else 121
+    ns = [759, 300, 515]
+    dev = torch.device("cuda")
+    Wf = [torch.ones((D, h), device=dev), torch.ones((h, h), device=dev), torch.ones((h, C), device=dev)]
+
+    def weights(ops):
+        return (ops.val2bit(Wf[0], bits, True, False), ops.val2bit(Wf[1], bits, True, False), ops.val2bit(Wf[2], bits, True, True), h, h, C)
+
+    A, X = [], []
+    for n in ns:
+        A.append((torch.rand((n, n), device=dev) < 0.02).float())
+        X.append(torch.randn((n, D), device=dev))
+    fwd = drv.gin_forward if run_gin else drv.gcn_forward
+    Wr = weights(ref)
+    want = [fwd(ref, ref.val2bit(a, 1, False, False), ref.val2bit(x, bits, True, False), Wr, n, D, bits) for a, x, n in zip(A, X, ns)]
+    Wo = weights(QGTC)
+    bA = [QGTC.val2bit(a, 1, False, False) for a in A]
+    bX = [QGTC.val2bit(x, bits, True, False) for x in X]
+    maps = [QGTC.tile_bitmap(a, n, n) for a, n in zip(bA, ns)]
+    for fused in (True, False):
+        got = drv.grouped_forward(QGTC, run_gin, bA, bX, maps, Wo, ns, D, bits, fused=fused)
+        torch.cuda.synchronize()
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert torch.equal(g, w), (i, ns[i], fused, float((g - w).abs().max()))
+    capfd.readouterr()
