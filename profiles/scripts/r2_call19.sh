@@ -1,0 +1,10 @@
+#!/bin/bash
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests/test_tc05_gpu.py -m gpu -q -x 2>&1 | tail -3 > $O/r2c19_tests.txt
+cat $O/r2c19_tests.txt
+QGTC_TC05_TRACE=1 QGTC_TC05_TRACE_F4=1 timeout 120 python profiles/scripts/tc05_trace.py 64 > $O/r2c19_trace_f4_n64.txt 2>&1
+head -30 $O/r2c19_trace_f4_n64.txt
+: > $O/r2c19_ab.txt
+timeout 300 python profiles/scripts/tc05_ab.py dense_issue quick >> $O/r2c19_ab.txt 2>&1
+cat $O/r2c19_ab.txt

@@ -86,6 +86,7 @@ struct Tc05Args {
     int amode;                      // 3 = 4-bit operand path (kind::mxf4, adjacency bit -> E2M1 nibble, features as E2M1); else adjacency expansion: 0 = bit -> 1 (shift + AND), 1 = bit -> 128 (IMAD + AND), 2 = bit c -> 2^(c%4) (AND only; feature rows pre-scaled)
     int ni;                         // number of MMA issuer warps (2..kMaxIssuers)
     unsigned int one;               // == 1, opaque to the compiler (keeps mul.hi from becoming a shift)
+    unsigned int epi_sleep;         // ns the epilogue warps sleep between polls of the accumulator barrier
     unsigned int* error_flag;       // device word set by the watchdog
     unsigned long long* trace;      // optional clock64 trace of CTA 0 (QGTC_TC05_TRACE=1), else null
 };
@@ -97,6 +98,7 @@ constexpr int kTraceItems = 512;    // per role: [item][8] timestamps
     } while (0)
 
 // PTX wrappers and the epilogue helpers live in tc05_common.cuh (shared with gemm_grp.cu)
+constexpr int kFlagsOff = (3 * kMaxStages + 2 * kRawSlots + 6) * 8;   // flag bytes after the mbarrier arrays
 struct SmemLayout {
     // offsets in bytes from the 1024-byte aligned base
     int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
@@ -110,7 +112,7 @@ __host__ __device__ inline SmemLayout smem_layout(int NP, int stages, int cps, i
     L.b_stage0 = L.raw0 + rslots * L.raw_slot_bytes;
     L.b_stage_bytes = cps * NP * ((pair || f4) ? 64 : 128);    // pair mode: each CTA holds half of the feature columns; 4-bit path: half the bytes
     L.bars = L.b_stage0 + stages * L.b_stage_bytes;
-    L.flags = L.bars + (3 * kMaxStages + 2 * kRawSlots + 6) * 8;
+    L.flags = L.bars + kFlagsOff;
     L.misc = L.flags + kMaxStages * 32;                // flags: [stage][chunk <= 8][lane quarter]
     L.total = L.misc + 32;
     return L;
@@ -297,14 +299,16 @@ __global__ void __launch_bounds__(256) prep_b4_kernel(GemmArgs P, uint8_t* __res
 // DBG = 2 adds the clock64 trace and the timing-experiment knobs (flag bits 0x10000..0x400000), DBG = 1 only the
 // trace (the production code path with seven clock reads per item, for timelines that can be trusted); the production
 // instance carries none of that code in its (latency-bound) role loops.
-template <int EPI, bool PAIR, int DBG, int AMODE>   // AMODE >= 0 fixes the expansion mode at compile time, -1 reads T.amode
+// CPST > 0 fixes the chunks per item at compile time (the hot configurations: 7 on the 4-bit path, 4 on the u8 path), so the
+// expander loop carries no per-chunk predicates or address arithmetic; 0 reads T.cps.
+template <int EPI, bool PAIR, int DBG, int AMODE, int CPST = 0>   // AMODE >= 0 fixes the expansion mode at compile time, -1 reads T.amode
 __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Args T, const __grid_constant__ CUtensorMap tmapA) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const GemmArgs& P = T.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = T.cps;
+    const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = CPST > 0 ? CPST : T.cps;
     constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
     constexpr int kCh = F4 ? kMaxCps4 : kMaxCps;          // chunks per item, compile-time bound
     constexpr int kChunkCols = F4 ? 16 : 32;              // TMEM columns of one expanded chunk
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // G <= S is required: a warp that reaches item X has seen the MMAs of item X-G-S complete (it waited for
         // them at item X-G), which only implies that item X-2S is done -- no mbarrier phase aliasing -- if G <= S
         // (MMA completion is in item order, see the issuers).  With three stages the fourth group idles.
-        const int WCH = T.wch;
+        const int WCH = (CPST > 0 && !QGTC_TC05_WIDE) ? CPST : T.wch;
         const int G = min(min(kProducerWarps / T.wpi, S), T.rslots);
         const int row = 32 * q + lane;             // row of the tile == TMEM lane
         const int my_items = g < G ? (n_items - g + G - 1) / G : 0;   // warps beyond the last group idle
@@ -428,7 +432,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
         const int trole = warp == 0 ? 0 : (warp == 1 ? 3 : (warp == 3 ? 4 : (warp == 8 ? 6 : -1)));
         const bool tr = DBG && (trole >= 0 && lane == 0);
-        volatile unsigned char* my_flags = flags + c0 * 4 + q;
+        // shared-window addresses, formed once: this lane's row in slot 0 (swizzled: bits [4, 4 + log2 cps) of the row offset
+        // are zero, so chunk j sits at (row address | swz << 4) ^ (j << 4)), this warp's flag bytes, the barrier arrays
+        const bool swizzled = CPS == 4 || CPS == 2;
+        const uint32_t raw_row0 = smem_u32(raw_slots) + row_off + (swizzled ? (swz << 4) : 0u);
+        const uint32_t slot_bytes = (uint32_t)L.raw_slot_bytes;
+        // (one base register: the barrier arrays and the flag bytes sit at constant offsets from the first barrier)
+        const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * kMaxStages, raw_full0 = full0 + 16u * kMaxStages, raw_empty0 = raw_full0 + 8u * kRawSlots;
+        const uint32_t flag_addr0 = full0 + (uint32_t)kFlagsOff + (uint32_t)(c0 * 4 + q + lane * 4);
+        auto lds128 = [](uint32_t addr) -> uint4 {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+            return v;
+        };
         // expansion of one 128-bit chunk of this lane's row into the 32 TMEM columns' registers
         auto expand = [&](const uint4& pv, uint32_t (&r)[32]) {
             const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -468,41 +484,48 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 r[4 * wd + 0] = w[wd] & 0x11111111u;
                 r[4 * wd + 1] = w[wd] & 0x22222222u;
                 r[4 * wd + 2] = w[wd] & 0x44444444u;
-                r[4 * wd + 3] = (w[wd] >> 1) & 0x44444444u;
+                r[4 * wd + 3] = (w[wd] >> 1) & 0x44444444u;   // (as IMAD.HI on the FMA pipe instead: measured 3 % slower)
             }
         };
-        auto is_nonzero = [&](const uint4& pv) -> bool {
-            return nojump || PAIR || __any_sync(0xffffffffu, (pv.x | pv.y | pv.z | pv.w) != 0u);
-        };
+        // zero-tile jumping on the fly: every lane notes which of its chunks are non-zero (two ORs, a predicate and a
+        // predicated OR per chunk); ONE warp reduction per item turns that into the per-chunk flags of this lane quarter
+        const bool check_zero = !(nojump || PAIR);
         for (int k = 0; k < my_items; ++k) {
             if (tr) QGTC_TRACE(trole, k, 0);
-            if (!dbg_no_ldg) mbar_wait(&raw_full[slot], raw_use & 1, T.error_flag, 7, hinted);
+            if (!dbg_no_ldg) mbar_wait_a(raw_full0 + 8u * (uint32_t)slot, raw_use & 1, T.error_flag, 7, hinted);
             uint4 v[kCh];
-            const unsigned char* src = raw_slots + (size_t)slot * L.raw_slot_bytes + row_off;
+            const uint32_t src = raw_row0 + (uint32_t)slot * slot_bytes;
+            auto load_chunk = [&](int j) -> uint4 {
+                return j < WCH ? lds128(swizzled ? (src ^ ((uint32_t)(c0 + j) << 4)) : (src + ((uint32_t)(c0 + j) << 4))) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            // 4-bit path: all chunks up front (16 result registers per chunk leave room); u8 path: one chunk ahead of the
+            // expansion (32 result registers per chunk: loading everything first spills the loop state)
+            constexpr int kAhead = F4 ? kCh : 2;
 #pragma unroll
-            for (int j = 0; j < kCh; ++j)
-                v[j] = j < WCH ? *reinterpret_cast<const uint4*>(src + (((uint32_t)(c0 + j) ^ swz) << 4)) : make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < kAhead; ++j) v[j] = load_chunk(j);
             if (tr) QGTC_TRACE(trole, k, 1);
             // expand the first chunk BEFORE waiting for the stage: the registers hold it while the MMAs of the
             // stage's previous use drain, so only the tcgen05.st sits behind the wait.  An all-zero 32 x 128 block is
             // expanded like any other (to zeros); it only clears its flag so that the MMA can be skipped when the
             // other three lane quarters are zero too.
-            unsigned nzmask = 0;
+            uint32_t lane_nz = 0;
             const uint32_t st_s = st_addr + (uint32_t)(s * stage_cols);
             if (F4) {
                 {
                     uint32_t r[16];
-                    if (is_nonzero(v[0])) nzmask |= 1u;
+                    if ((v[0].x | v[0].y | v[0].z | v[0].w) != 0u) lane_nz |= 1u;
                     expand4(v[0], r);
-                    mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
+                    if (tr) QGTC_TRACE(trole, k, 2);
+                    mbar_wait_a<32>(empty0 + 8u * (uint32_t)s, (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
                     tc_fence_after();
+                    if (tr) QGTC_TRACE(trole, k, 3);
                     tmem_st16r(st_s, r);
                 }
 #pragma unroll
                 for (int j = 1; j < kCh; ++j) {
                     if (j < WCH) {   // warp-uniform
                         uint32_t r[16];
-                        if (is_nonzero(v[j])) nzmask |= 1u << j;
+                        if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) lane_nz |= 1u << j;
                         expand4(v[j], r);
                         tmem_st16r(st_s + (uint32_t)(16 * j), r);
                     }
@@ -510,10 +533,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             } else {
                 {
                     uint32_t r[32];
-                    if (is_nonzero(v[0])) nzmask |= 1u;
+                    if ((v[0].x | v[0].y | v[0].z | v[0].w) != 0u) lane_nz |= 1u;
                     expand(v[0], r);
                     if (tr) QGTC_TRACE(trole, k, 2);
-                    mbar_wait<32>(&empty[s], (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
+                    mbar_wait_a<32>(empty0 + 8u * (uint32_t)s, (use & 1) ^ 1, T.error_flag, 1, hinted);   // the MMAs of the previous use of this stage are done
                     tc_fence_after();
                     if (tr) QGTC_TRACE(trole, k, 3);
                     if (!dbg_no_st) tmem_st32(st_s, r);
@@ -521,25 +544,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 }
 #pragma unroll
                 for (int j = 1; j < kCh; ++j) {
+                    if (j + 1 < kCh) v[j + 1] = load_chunk(j + 1);
                     if (j < WCH) {   // warp-uniform
                         uint32_t r[32];
-                        if (is_nonzero(v[j])) nzmask |= 1u << j;
+                        if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) lane_nz |= 1u << j;
                         expand(v[j], r);
                         if (!dbg_no_st) tmem_st32(st_s + (uint32_t)(32 * j), r);
                         else if (r[5] == 0xdeadbeefu) flags[255] = 1;
                     }
                 }
             }
-            // every lane holds its raw words by now (the votes of the expansions needed them): the slot can be refilled
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[slot]);
-            if (lane < WCH) my_flags[s * 32 + lane * 4] = (unsigned char)((nzmask >> lane) & 1u);
+            // every lane holds its raw words by now: the slot can be refilled
+            const uint32_t nzmask = check_zero ? __reduce_or_sync(0xffffffffu, lane_nz) : 0xffffffffu;   // also converges the warp
+            if (!check_zero) __syncwarp();
+            if (lane == 0) mbar_arrive_a(raw_empty0 + 8u * (uint32_t)slot);
+            if (lane < WCH) {
+                const uint32_t bit = (nzmask >> lane) & 1u;
+                asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(flag_addr0 + 32u * (uint32_t)s), "r"(bit) : "memory");
+            }
             if (tr) QGTC_TRACE(trole, k, 4);
             if (!dbg_no_st) tmem_wait_st();
             tc_fence_before();
             if (tr) QGTC_TRACE(trole, k, 5);
             __syncwarp();   // every lane's tcgen05.st has completed, the flags are written
-            if (lane == 0) mbar_arrive(&full[s]);
+            if (lane == 0) mbar_arrive_a(full0 + 8u * (uint32_t)s);
             if (tr) QGTC_TRACE(trole, k, 6);
             slot += G;
             if (slot >= rslots) { slot -= rslots; ++raw_use; }
@@ -785,7 +813,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
             const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
-            mbar_wait<512>(&d_full[buf], duse & 1, T.error_flag, 6, false);   // long wait (a whole tile): sleep between polls instead of the hinted try_wait, which wakes at every barrier event of the CTA
+            {   // long wait (a whole tile): sleep between polls instead of the hinted try_wait, which wakes at every barrier event of the CTA
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&d_full[buf], duse & 1)) {
+                    __nanosleep(T.epi_sleep);
+                    if (++spins > (1u << 24)) {
+                        if (T.error_flag) { atomicExch_system(T.error_flag, 0x80000000u | 6u); __threadfence_system(); }
+                        __trap();
+                    }
+                }
+            }
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
@@ -922,7 +959,8 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     static const bool f4_env = [] { const char* e = getenv("QGTC_TC05_FP4"); return !(e && e[0] == '0'); }();
     static const bool trace_env = [] { const char* t = getenv("QGTC_TC05_TRACE"); return t && t[0] == '1'; }();
     const double max_sum = (double)a.gdk * 128.0 * (double)((1u << a.bit2) - 1u);
-    const bool f4 = f4_env && !trace_env && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && max_sum < 8388608.0;
+    static const bool trace_f4_env = [] { const char* t = getenv("QGTC_TC05_TRACE_F4"); return t && t[0] == '1'; }();   // trace the 4-bit path instead of the u8 path
+    const bool f4 = f4_env && (!trace_env || trace_f4_env) && !pair && (a.flags & 0x6F0000u) == 0 && a.bit2 <= 2 && max_sum < 8388608.0;
     if (f4) {
         // chunks per item: the largest of {7, 5, 4, 3, 2, 1} that fits three stages and K (6 and 8 chunks would put the
         // 128 rows of a raw slot on a stride with shared-memory bank conflicts; 4 and 2 use the TMA swizzle)
@@ -966,6 +1004,10 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
     T.units = pair ? T.spg * a.count : T.total_tiles;
     T.epi = epi;
     T.one = 1u;
+    {
+        static const int sleep_env = [] { const char* e = getenv("QGTC_TC05_EPI_SLEEP"); return e ? atoi(e) : 0; }();
+        T.epi_sleep = sleep_env > 0 ? (unsigned)sleep_env : 512u;
+    }
     {
         static const int ni_env = [] { const char* e = getenv("QGTC_TC05_ISSUERS"); return e ? atoi(e) : 0; }();
         T.ni = (ni_env >= 1 && ni_env <= kMaxIssuers) ? ni_env : 2;
@@ -1096,18 +1138,29 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             return check_launch("gemm_tc05_kernel");
         };
         const bool knobs = (T.g.flags & 0x6F0000u) != 0, trace = T.trace != nullptr;
+        // compile-time chunks per item for the hot configurations (QGTC_TC05_FIXED=0: the runtime-cps instances, for A/B runs)
+        static const bool fixed_env = [] { const char* e = getenv("QGTC_TC05_FIXED"); return !(e && e[0] == '0'); }();
+        const bool fixed_ok = fixed_env && !QGTC_TC05_WIDE && T.wch == T.cps;
         const bool fl = epi == kEpiFloat;
         if (knobs) {
             if (pair) rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, 2, -1>);
             else rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
         } else if (pair) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, true, 0, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, true, 0, -1>);
+        } else if (T.amode == 3 && T.cps == 7 && fixed_ok && trace && !fl) {
+            rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 3, 7>);    // the production code path + clock reads
+        } else if (T.amode == 3 && T.cps == 7 && fixed_ok) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 3, 7>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 3, 7>);
         } else if (T.amode == 3) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 3>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 3>);
         } else if (trace && !fl && T.amode == 2) {
             rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2>);       // the production code path + clock reads
         } else if (trace) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
+        } else if (T.amode == 2 && T.cps == 4 && fixed_ok) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 2, 4>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 2, 4>);
+        } else if (T.amode == 1 && T.cps == 4 && fixed_ok) {
+            rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 1, 4>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 1, 4>);
         } else if (T.amode == 2) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 2>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 2>);
         } else if (T.amode == 1) {

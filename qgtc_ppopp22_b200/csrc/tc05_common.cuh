@@ -72,6 +72,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
         }
     }
 }
+// The same operations on a shared-window address formed once by the caller (role loops: no generic-to-shared conversion per use)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+template <int kBackoffNs = 0>
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, unsigned int* error_flag, int where, bool hinted = false) {
+    uint32_t spins = 0;
+    if (hinted) {
+        while (!mbar_try_wait_hint_a(bar, parity, 1000000u)) {
+            if (++spins > (1u << 16)) {
+                if (error_flag) { atomicExch_system(error_flag, 0x80000000u | (unsigned)where); __threadfence_system(); }
+                __trap();
+            }
+        }
+        return;
+    }
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (kBackoffNs > 0) __nanosleep(kBackoffNs);
+        if (++spins > (1u << 24)) {
+            if (error_flag) { atomicExch_system(error_flag, 0x80000000u | (unsigned)where); __threadfence_system(); }
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -246,8 +292,19 @@ __device__ __forceinline__ uint32_t requant_keep(int acc, int mx, unsigned keep)
 // FAST (accumulators = 2^dshift x sum with dshift <= 3, non-negative, ob <= 4): clamp to 2^dshift (2^ob + 1) so that every
 // value fits a byte, gather the four low bytes with three PRMTs and finish byte-parallel: >> dshift; the byte 2^ob + 1 ("above the range")
 // becomes 2^ob - 1, the byte 2^ob becomes 0 (reference kernel.h:31-37,350), everything else passes.
-template <bool NN, bool FAST>
+// F4RAW (with FAST): the inputs are the bit patterns of f32 sums (exact non-negative integers): clamp as floats and add the magic
+// number 2^23 -- the low byte of the result is the clamped value and bytes 1-2 are zero, which is all the byte gather reads
+template <bool NN, bool FAST, bool F4RAW = false>
 __device__ __forceinline__ uint32_t requant4(int a0, int a1, int a2, int a3, int dshift, int ob, int mx, unsigned keep) {
+    if (FAST && F4RAW) {
+        const float lim = (float)(mx + 1);
+        const uint32_t t0 = __float_as_uint(fminf(__int_as_float(a0), lim) + 8388608.0f), t1 = __float_as_uint(fminf(__int_as_float(a1), lim) + 8388608.0f);
+        const uint32_t t2 = __float_as_uint(fminf(__int_as_float(a2), lim) + 8388608.0f), t3 = __float_as_uint(fminf(__int_as_float(a3), lim) + 8388608.0f);
+        const uint32_t lo = __byte_perm(t0, t1, 0x1140u), hi = __byte_perm(t2, t3, 0x1140u);
+        const uint32_t four = __byte_perm(lo, hi, 0x5410u);
+        const uint32_t over = (four >> ob) & four & 0x01010101u;
+        return (four & (keep * 0x01010101u)) | (over * keep);
+    }
     if (FAST) {
         const int lim = (mx + 1) << dshift;
         const uint32_t t0 = (uint32_t)min(a0, lim), t1 = (uint32_t)min(a1, lim), t2 = (uint32_t)min(a2, lim), t3 = (uint32_t)min(a3, lim);
@@ -279,7 +336,7 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             int v0[16], v1[16];
             tmem_ld16(d_tmem + 32 * w, v0);
             tmem_ld16(d_tmem + 32 * w + 16, v1);
-            if (F4) {
+            if (F4 && !FAST) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     v0[e] = __float_as_int(__int_as_float(v0[e]) + 8388608.0f) - 0x4B000000;
@@ -291,8 +348,8 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             for (int g = 0; g < 4; ++g) {
                 const int* vv = g < 2 ? &v0[8 * g] : &v1[8 * (g - 2)];
                 // the transpose wants the first column in the top byte: reverse the four bytes
-                uint32_t x = __byte_perm(requant4<NN, FAST>(vv[0], vv[1], vv[2], vv[3], dshift, ob, mx, keep), 0u, 0x0123u);
-                uint32_t y = __byte_perm(requant4<NN, FAST>(vv[4], vv[5], vv[6], vv[7], dshift, ob, mx, keep), 0u, 0x0123u);
+                uint32_t x = __byte_perm(requant4<NN, FAST, F4>(vv[0], vv[1], vv[2], vv[3], dshift, ob, mx, keep), 0u, 0x0123u);
+                uint32_t y = __byte_perm(requant4<NN, FAST, F4>(vv[4], vv[5], vv[6], vv[7], dshift, ob, mx, keep), 0u, 0x0123u);
                 transpose8x8(x, y);
                 xs[g] = x;
                 ys[g] = y;
@@ -316,14 +373,14 @@ __device__ __forceinline__ void epi_bits_tile(uint32_t d_tmem, int NP, int half,
             const int cb = 2 * w + hcb;
             int v[16];
             tmem_ld16(d_tmem + 16 * cb, v);
-            if (F4) {
+            if (F4 && !FAST) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = __float_as_int(__int_as_float(v[e]) + 8388608.0f) - 0x4B000000;
             }
             const bool whole = 16 * cb + 16 <= N;   // else: one byte mask per four values
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-                uint32_t four = requant4<NN, FAST>(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3], dshift, ob, mx, keep);
+                uint32_t four = requant4<NN, FAST, F4>(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3], dshift, ob, mx, keep);
                 uint32_t mask = rmask;
                 if (!whole) {
                     const int nv = N - (16 * cb + 4 * g4);   // valid columns of this group of four
