@@ -35,6 +35,13 @@ if __name__ == "__main__":
             r = mm[i]
             if r[0]:
                 print("  %3d  %6d %6d %6d |  (t=%d)" % (i, r[4] - r[0], r[1] - r[4], r[3] - r[1], r[0] - t0))
+    for role, name in ((1, "MMA issuer 0"), (5, "MMA issuer 1")):
+        mm = t[role]
+        print(name + " (items of the other issuer): item  t_begin_wait  wait_full")
+        for i in range(20, 36):
+            r = mm[i]
+            if r[5]:
+                print("  %3d  %8d %6d" % (i, r[5] - t0, r[6] - r[5]))
     for role, name in ((0, "expander warp 0 (group 0, SMSP0)"), (3, "expander warp 1 (group 0, SMSP1)"), (4, "expander warp 3 (group 0, SMSP3)"), (6, "expander warp 8 (group 1, SMSP0)")):
         pr = t[role]
         print(name + " own items: rawwait+lds  expand0  wait_empty  st+expand1+st  wait_st  flags+arrive | period (t_start, t_arrive)")

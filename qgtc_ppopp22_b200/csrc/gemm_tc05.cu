@@ -52,7 +52,7 @@ constexpr int kEpiStep = kEpilogueWarps / 4;   // epilogue warps per TMEM lane q
 constexpr int kLoaderWarp = kEpilogueWarp0 + kEpilogueWarps;
 constexpr int kALoaderWarp = kLoaderWarp + 1;
 constexpr int kMmaWarp = kLoaderWarp + 2;      // first MMA issuer (also allocates TMEM); issuer i is warp kMmaWarp + i
-constexpr int kMaxIssuers = 2;    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
+constexpr int kMaxIssuers = 2;    // (the per-owner `full` barriers below assume at most two)    // Tc05Args::ni of them are launched; they take the pipeline items round-robin
 constexpr int kMmaWarp2 = kMmaWarp + 1;
 constexpr int kMaxThreads = (kMmaWarp + kMaxIssuers) * 32;
 constexpr int kRawSlots = 8;      // TMA ring of packed adjacency tiles (128 rows x 16*cps bytes each)
@@ -61,6 +61,18 @@ constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
 constexpr int kMaxCps4 = 8;       // ... 4-bit operand path (a chunk takes 16 TMEM columns instead of 32)
 constexpr int kSfCols = 16;       // 4-bit path: TMEM columns holding the (all-ones) block scale factors: 4 for A, 12 for B (N up to 256)
 constexpr int kTmemCols = 512;
+#ifndef QGTC_TC05_SPLIT
+#define QGTC_TC05_SPLIT 0
+#endif
+#ifndef QGTC_TC05_DENSE_ISSUE
+#define QGTC_TC05_DENSE_ISSUE 1
+#endif
+#ifndef QGTC_TC05_OWN_FULL
+#define QGTC_TC05_OWN_FULL 1
+#endif
+#ifndef QGTC_TC05_OWNER_COMMIT
+#define QGTC_TC05_OWNER_COMMIT 1
+#endif
 
 struct Tc05Args {
     GemmArgs g;
@@ -98,7 +110,7 @@ constexpr int kTraceItems = 512;    // per role: [item][8] timestamps
     } while (0)
 
 // PTX wrappers and the epilogue helpers live in tc05_common.cuh (shared with gemm_grp.cu)
-constexpr int kFlagsOff = (3 * kMaxStages + 2 * kRawSlots + 6) * 8;   // flag bytes after the mbarrier arrays
+constexpr int kFlagsOff = (5 * kMaxStages + 2 * kRawSlots + 6) * 8;   // flag bytes after the mbarrier arrays
 struct SmemLayout {
     // offsets in bytes from the 1024-byte aligned base
     int raw0, raw_slot_bytes, b_stage0, b_stage_bytes, bars, flags, misc, total;
@@ -310,6 +322,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = CPST > 0 ? CPST : T.cps;
     constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
+    // Split release (compile-time item size, no pairing): the issuer commits to `empty` after the MMAs of the first kHalf chunks
+    // of an item and to `empty2` after the rest, so the expanders refill the first chunks of a stage while the tensor pipe
+    // still works on its last ones -- the ring (three stages: fill + pick-up + drain + release = three drains) gets slack.
+    // Only the owner of an item commits to its `empty` barrier (not in pair mode).  Every issuer still WAITS for every item's
+    // `full` phase (parity waits must not skip a phase), but a non-owner's tcgen05.commit would queue behind the owner's MMAs
+    // in the tensor-core instruction queue and stall that warp until they are dispatched (clock64 trace: its own next item was
+    // picked up 300-450 cycles late, the tensor pipe idling meanwhile).  Every other waiter of `empty[s]` sees every phase of
+    // it (an expander group stays on one stage because G == S; the feature loader walks all items), so completion order
+    // between the issuers does not matter.
+    constexpr bool kOwnerCommit = !PAIR && !QGTC_TC05_WIDE && QGTC_TC05_OWNER_COMMIT;   // (the wide layout has G < S)
+    // Per-owner `full` barriers (not in pair mode): item i is signalled on full[s] when issuer 0 owns it and on full_b[s] when
+    // issuer 1 does, so an issuer meets consecutive phases of every barrier it waits on and never has to observe the other
+    // issuer's items (with one barrier per stage it had to: a parity wait must not skip a phase, and every such wait costs
+    // ~160 cycles even on a completed barrier -- clock64 trace, profiles/r2_tc05_trace_f4_n64_call25.txt).
+    constexpr bool kOwnFull = kOwnerCommit && QGTC_TC05_OWN_FULL;   // (a non-owner that skips an item cannot commit to its `empty` barrier either)
+    constexpr bool SPLIT = CPST > 1 && !PAIR && QGTC_TC05_SPLIT;
+    constexpr int kHalf = SPLIT ? (CPST + 1) / 2 : 0;
     constexpr int kCh = F4 ? kMaxCps4 : kMaxCps;          // chunks per item, compile-time bound
     constexpr int kChunkCols = F4 ? 16 : 32;              // TMEM columns of one expanded chunk
     const SmemLayout L = smem_layout(NP, S, CPS, PAIR ? 1 : 0, T.rslots, F4 ? 1 : 0);
@@ -328,13 +357,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     uint64_t* d_empty = d_full + 2;                 // [2] epilogue -> MMA   (count 8 warps)
     uint64_t* peer_full = d_empty + 2;              // [kMaxStages] pair mode, leader only: the peer CTA's stage is ready (relayed)
     uint64_t* peer_dempty = peer_full + kMaxStages; // [2]          pair mode, leader only: the peer's epilogue drained the accumulator
+    uint64_t* empty2 = peer_dempty + 2;             // [kMaxStages] split release (SPLIT): the MMAs of the second half of the stage's chunks are done
+    uint64_t* full_b = empty2 + kMaxStages;         // [kMaxStages] per-owner `full` barriers (kOwnFull): the items of issuer 1 (issuer 0's use `full`)
+    constexpr uint32_t kFullBOff = (uint32_t)(4 * kMaxStages + 2 * kRawSlots + 6) * 8u;   // byte offset of full_b from full
     volatile unsigned char* flags = smem_raw + L.flags;  // [stage][chunk][lane quarter]: that expander warp's 32 x 128 bits are non-zero
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.misc);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&full[s], T.wpi + 1);         // the expander warps of one item + the feature copy's expect_tx
-            mbar_init(&empty[s], T.ni);             // every MMA issuer commits every item (see the issuer loop)
+            mbar_init(&full_b[s], T.wpi + 1);
+            mbar_init(&empty[s], kOwnerCommit ? 1 : T.ni);   // the item's owner commits (pair mode: every issuer, see the issuer loop)
+            mbar_init(&empty2[s], kOwnerCommit ? 1 : T.ni);
         }
         for (int s = 0; s < kRawSlots; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -427,6 +461,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 
         const int rslots = T.rslots;
         int slot = g % rslots, s = g % S;          // raw ring slot and TMEM/B stage of the current item
+        int own = kOwnFull ? g % T.ni : 0;         // issuer that owns the current item (item % ni)
+        const int own_step = kOwnFull ? G % T.ni : 0;
         uint32_t raw_use = (uint32_t)(g / rslots), use = (uint32_t)(g / S);
         const uint32_t st_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(dcols + kChunkCols * c0);
         // traced expander warps: 0 (role 0), 1 (role 3), 3 (role 4), 8 (role 6)
@@ -440,6 +476,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // (one base register: the barrier arrays and the flag bytes sit at constant offsets from the first barrier)
         const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * kMaxStages, raw_full0 = full0 + 16u * kMaxStages, raw_empty0 = raw_full0 + 8u * kRawSlots;
         const uint32_t flag_addr0 = full0 + (uint32_t)kFlagsOff + (uint32_t)(c0 * 4 + q + lane * 4);
+        const uint32_t empty2_0 = smem_u32(empty2);
         auto lds128 = [](uint32_t addr) -> uint4 {
             uint4 v;
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -523,6 +560,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 }
 #pragma unroll
                 for (int j = 1; j < kCh; ++j) {
+                    if (SPLIT && j == kHalf) {   // the second half of the stage's previous use has been multiplied too
+                        mbar_wait_a<32>(empty2_0 + 8u * (uint32_t)s, (use & 1) ^ 1, T.error_flag, 14, hinted);
+                        tc_fence_after();
+                    }
                     if (j < WCH) {   // warp-uniform
                         uint32_t r[16];
                         if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) lane_nz |= 1u << j;
@@ -545,6 +586,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
 #pragma unroll
                 for (int j = 1; j < kCh; ++j) {
                     if (j + 1 < kCh) v[j + 1] = load_chunk(j + 1);
+                    if (SPLIT && j == kHalf) {   // the second half of the stage's previous use has been multiplied too
+                        mbar_wait_a<32>(empty2_0 + 8u * (uint32_t)s, (use & 1) ^ 1, T.error_flag, 14, hinted);
+                        tc_fence_after();
+                    }
                     if (j < WCH) {   // warp-uniform
                         uint32_t r[32];
                         if ((v[j].x | v[j].y | v[j].z | v[j].w) != 0u) lane_nz |= 1u << j;
@@ -567,12 +612,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             tc_fence_before();
             if (tr) QGTC_TRACE(trole, k, 5);
             __syncwarp();   // every lane's tcgen05.st has completed, the flags are written
-            if (lane == 0) mbar_arrive_a(full0 + 8u * (uint32_t)s);
+            if (lane == 0) mbar_arrive_a(full0 + (own ? kFullBOff : 0u) + 8u * (uint32_t)s);
             if (tr) QGTC_TRACE(trole, k, 6);
             slot += G;
             if (slot >= rslots) { slot -= rslots; ++raw_use; }
             s += G;
             if (s >= S) { s -= S; ++use; }
+            own += own_step;
+            if (own >= T.ni) own -= T.ni;
         }
     } else if (warp == kALoaderWarp) {
         // ===================== adjacency TMA loader =====================
@@ -603,7 +650,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             // of prep_b_kernel; the image itself is complete and visible only after this wait
             asm volatile("griddepcontrol.wait;\n" ::: "memory");
             const uint32_t chunk_bytes = (uint32_t)NP * (F4 ? 64u : 128u);
-            int s = 0;
+            int s = 0, own = 0;       // own: issuer that owns the item (item % ni), selects the `full` barrier
             uint32_t use = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int u = group_id + tl * ngroups;
@@ -614,9 +661,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                 for (int st; (st = it.next<PAIR>(T, u, CPS, gdk)) >= 0;) {
                     const int c0 = st * CPS;
                     const int nch = (gdk - c0 < CPS) ? gdk - c0 : CPS;
-                    mbar_wait<128>(&empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);
+                    mbar_wait<128>(SPLIT ? &empty2[s] : &empty[s], (use & 1) ^ 1, T.error_flag, 2, hinted);   // every MMA that reads the stage's feature chunks is done
+                    uint64_t* fbar = (kOwnFull && own) ? &full_b[s] : &full[s];
+                    if (kOwnFull && ++own == T.ni) own = 0;
                     if (dbg_no_bulk) {
-                        mbar_arrive(&full[s]);
+                        mbar_arrive(fbar);
                     } else if (PAIR) {
                         // this CTA's half of every chunk (the image keeps the two halves of a chunk apart)
                         const uint32_t half_bytes = chunk_bytes >> 1;
@@ -625,8 +674,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                             bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes + (size_t)j * half_bytes,
                                      img + (unsigned long long)(c0 + j) * chunk_bytes + (unsigned long long)rank * half_bytes, half_bytes, &full[s]);
                     } else {
-                        mbar_expect_tx(&full[s], chunk_bytes * (uint32_t)nch);
-                        bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, &full[s]);
+                        mbar_expect_tx(fbar, chunk_bytes * (uint32_t)nch);
+                        bulk_g2s(b_stages + (size_t)s * L.b_stage_bytes, img + (unsigned long long)c0 * chunk_bytes, chunk_bytes * (uint32_t)nch, fbar);
                     }
                     if (++s == S) { s = 0; ++use; }
                 }
@@ -692,8 +741,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const uint32_t kstep_lo = (2u * lbo) >> 4;   // one MMA's K: two core matrices (u8: 2 x 16 elements, 4-bit: 2 x 32)
             int s = 0, buf = 0, item = 0, owner = 0;   // owner = item % T.ni
             uint32_t use = 0, duse = 0;
+            uint32_t own_par = 0;   // kOwnFull: bit s = parity of this issuer's next wait on its `full` barrier of stage s
             auto acquire = [&](int s_, uint32_t use_) -> uint32_t {
-                mbar_wait(&full[s_], use_ & 1, T.error_flag, 4, hinted);
+                if (kOwnFull) {
+                    mbar_wait(who ? &full_b[s_] : &full[s_], (own_par >> s_) & 1u, T.error_flag, 4, hinted);
+                    own_par ^= 1u << s_;
+                } else {
+                    mbar_wait(&full[s_], use_ & 1, T.error_flag, 4, hinted);
+                }
                 if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 4);
                 if (PAIR) {   // ... and the peer CTA's half of the stage; its zero flags are not visible here: issue everything
                     mbar_wait(&peer_full[s_], use_ & 1, T.error_flag, 11, hinted);
@@ -725,8 +780,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
                         const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
                         if (elect_one()) {
+                            if (CPST > 0 && !SPLIT && QGTC_TC05_DENSE_ISSUE && nch == CPST && m_cur == ((1u << CPST) - 1u)) {
+                                // dense item of the compile-time size (the common case): one branch-free MMA sequence -- the issuer
+                                // warp gets an issue slot every 5-10 cycles next to the expanders, so its instruction count per
+                                // item, not the tensor pipe, sets the pick-up latency
+#pragma unroll
+                                for (int j = 0; j < (CPST > 0 ? CPST : 1); ++j) {
+                                    if (F4) {
+#pragma unroll
+                                        for (int mm = 0; mm < 2; ++mm) {
+                                            const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)mm * kstep_lo);
+                                            mma_f4_ts(d_tmem, a_tmem + (uint32_t)(16 * j + 8 * mm), desc, idesc, sfa, sfb, 1u);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int ks = 0; ks < 4; ++ks) {
+                                            const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(lo_s + (uint32_t)j * chunk_lo + (uint32_t)ks * kstep_lo);
+                                            mma_i8_ts(d_tmem, a_tmem + (uint32_t)(32 * j + 8 * ks), desc, idesc, 1u);
+                                        }
+                                    }
+                                }
+                            } else
 #pragma unroll
                             for (int j = 0; j < kCh; ++j) {
+                                if (SPLIT && j == kHalf) tc_commit(&empty[s]);   // the first chunks of the stage may be refilled
                                 if (j < nch && ((m_cur >> j) & 1u)) {
                                     if (F4) {   // two MMAs of K = 64 per 128-bit chunk (8 TMEM columns, two 32-element core matrices each)
 #pragma unroll
@@ -747,18 +824,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                             }
                             // arrives when these MMAs have finished reading A (TMEM) and B (smem); pair: in both CTAs
                             if (PAIR) tc_commit_pair(&empty[s]);
-                            else tc_commit(&empty[s]);
+                            else tc_commit(SPLIT ? &empty2[s] : &empty[s]);
                         }
                         __syncwarp();
                         if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 3);
-                    } else {
+                    } else if (!kOwnFull) {
                         // not this issuer's item: observe its phase and add this issuer's (in-order) commit
+                        if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 5);
                         mbar_wait(&full[s], use & 1, T.error_flag, 13, hinted);
-                        if (elect_one()) {
-                            if (PAIR) tc_commit_pair(&empty[s]);
-                            else tc_commit(&empty[s]);
+                        if (lane == 0 && trole >= 0) QGTC_TRACE(trole, item, 6);
+                        if (!kOwnerCommit) {
+                            if (elect_one()) {
+                                if (PAIR) tc_commit_pair(&empty[s]);
+                                else tc_commit(&empty[s]);
+                                if (SPLIT) tc_commit(&empty2[s]);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                     if (++owner == T.ni) owner = 0;
                     if (++s == S) { s = 0; ++use; }
@@ -1153,8 +1235,10 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 3, 7>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 3, 7>);
         } else if (T.amode == 3) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 0, 3>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 0, 3>);
+        } else if (trace && !fl && T.amode == 2 && T.cps == 4 && fixed_ok) {
+            rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2, 4>);    // the production code path + clock reads
         } else if (trace && !fl && T.amode == 2) {
-            rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2>);       // the production code path + clock reads
+            rc = launch(gemm_tc05_kernel<kEpiBitsRow, false, 1, 2>);
         } else if (trace) {
             rc = fl ? launch(gemm_tc05_kernel<kEpiFloat, false, 2, -1>) : launch(gemm_tc05_kernel<kEpiBitsRow, false, 2, -1>);
         } else if (T.amode == 2 && T.cps == 4 && fixed_ok) {
