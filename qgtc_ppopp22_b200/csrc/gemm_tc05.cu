@@ -61,6 +61,9 @@ constexpr int kMaxCps = 4;        // K chunks (128 bits each) per pipeline stage
 constexpr int kMaxCps4 = 8;       // ... 4-bit operand path (a chunk takes 16 TMEM columns instead of 32)
 constexpr int kSfCols = 16;       // 4-bit path: TMEM columns holding the (all-ones) block scale factors: 4 for A, 12 for B (N up to 256)
 constexpr int kTmemCols = 512;
+// split release of a stage (first / second half of its chunks): built and measured on B200 -- parity-green, 4 % slower on the
+// u8 path (the second wait sits in the middle of the fill and the extra state spills), no change on the 4-bit path; kept as a
+// compile-time experiment (-DQGTC_TC05_SPLIT=1), profiles/r2_tc05_ab_call23_split_release.txt, r2_tc05_ab_call29_split_u8.txt
 #ifndef QGTC_TC05_SPLIT
 #define QGTC_TC05_SPLIT 0
 #endif
@@ -322,9 +325,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = CPST > 0 ? CPST : T.cps;
     constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
-    // Split release (compile-time item size, no pairing): the issuer commits to `empty` after the MMAs of the first kHalf chunks
-    // of an item and to `empty2` after the rest, so the expanders refill the first chunks of a stage while the tensor pipe
-    // still works on its last ones -- the ring (three stages: fill + pick-up + drain + release = three drains) gets slack.
     // Only the owner of an item commits to its `empty` barrier (not in pair mode).  Every issuer still WAITS for every item's
     // `full` phase (parity waits must not skip a phase), but a non-owner's tcgen05.commit would queue behind the owner's MMAs
     // in the tensor-core instruction queue and stall that warp until they are dispatched (clock64 trace: its own next item was
@@ -337,7 +337,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     // issuer's items (with one barrier per stage it had to: a parity wait must not skip a phase, and every such wait costs
     // ~160 cycles even on a completed barrier -- clock64 trace, profiles/r2_tc05_trace_f4_n64_call25.txt).
     constexpr bool kOwnFull = kOwnerCommit && QGTC_TC05_OWN_FULL;   // (a non-owner that skips an item cannot commit to its `empty` barrier either)
-    constexpr bool SPLIT = CPST > 1 && !PAIR && QGTC_TC05_SPLIT;
+    // Split release (compile-time item size, no pairing): the issuer commits to `empty` after the MMAs of the first kHalf chunks
+    // of an item and to `empty2` after the rest, so the expanders refill the first chunks of a stage while the tensor pipe
+    // still works on its last ones -- the ring (three stages: fill + pick-up + drain + release = three drains) gets slack.
+    constexpr bool SPLIT = CPST > 1 && !PAIR && !F4 && QGTC_TC05_SPLIT;   // (the 4-bit path is paced by the MMA dispatch rate, not by the ring)
     constexpr int kHalf = SPLIT ? (CPST + 1) / 2 : 0;
     constexpr int kCh = F4 ? kMaxCps4 : kMaxCps;          // chunks per item, compile-time bound
     constexpr int kChunkCols = F4 ? 16 : 32;              // TMEM columns of one expanded chunk
@@ -780,12 +783,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                         const uint32_t a_tmem = tb + (uint32_t)(dcols + s * stage_cols);
                         const uint32_t lo_s = lo0 + (uint32_t)s * stage_lo;
                         if (elect_one()) {
-                            if (CPST > 0 && !SPLIT && QGTC_TC05_DENSE_ISSUE && nch == CPST && m_cur == ((1u << CPST) - 1u)) {
+                            if (CPST > 0 && QGTC_TC05_DENSE_ISSUE && nch == CPST && m_cur == ((1u << CPST) - 1u)) {
                                 // dense item of the compile-time size (the common case): one branch-free MMA sequence -- the issuer
                                 // warp gets an issue slot every 5-10 cycles next to the expanders, so its instruction count per
                                 // item, not the tensor pipe, sets the pick-up latency
 #pragma unroll
                                 for (int j = 0; j < (CPST > 0 ? CPST : 1); ++j) {
+                                    if (SPLIT && j == kHalf) tc_commit(&empty[s]);   // the first chunks of the stage may be refilled
                                     if (F4) {
 #pragma unroll
                                         for (int mm = 0; mm < 2; ++mm) {
