@@ -327,12 +327,12 @@ def run_ours(args):
     if u8_bits:
         a_u8 = sum(tops_k[b] for b in u8_bits) / len(u8_bits)
         by_path["u8_kind_i8"] = {"bits": u8_bits, "achieved": round(a_u8, 1), "peak": round(int8_peak, 1), "frac": round(a_u8 / int8_peak, 4),
-                                 "unit": "TOPS", "limiter": "adjacency expanders (ALU pipe 56-64 %) + 3-stage TMEM ring latency; tensor pipe 46-55 % active (ncu, profiles/r1_tc05_ncu_summary.txt)"}
+                                 "unit": "TOPS", "limiter": "three-stage TMEM ring: adjacency fill (CUDA-core bit -> byte expansion, ALU pipe 50-59 %) + MMA pick-up + drain per stage; tensor pipe 46-56 % active (ncu profiles/r2_tc05_ncu_summary_call31.txt, clock64 trace profiles/r2_tc05_trace_u8_n64_call27.txt); i8 dispatch floor 32 cycles / MMA at N = 64 (profiles/r2_mma_dispatch_rate_call20.txt)"}
     if fp4_bits:
         a_f4 = sum(tops_k[b] for b in fp4_bits) / len(fp4_bits)
         by_path["fp4_kind_mxf4"] = {"bits": fp4_bits, "achieved": round(a_f4, 1), "peak": round(fp4_peak, 1), "frac": round(a_f4 / fp4_peak, 4),
                                     "frac_of_int8_equivalent_peak": round(a_f4 / int8_peak, 4), "unit": "TOPS",
-                                    "limiter": "adjacency expanders (ALU pipe 65-68 %), DRAM 42 %; tensor pipe 37-39 % active (ncu)"}
+                                    "limiter": "tcgen05.mma kind::mxf4 dispatch rate: 42-44 cycles per instruction for any N <= 64 measured alone, 50-57 under load (profiles/r2_mma_dispatch_rate_call20.txt, clock64 trace profiles/r2_tc05_trace_f4_n64_call26.txt): the MMA phases of consecutive items run back to back; ALU pipe 59-63 %, DRAM 44 %, tensor math 42-43 % active (ncu profiles/r2_tc05_ncu_summary_call31.txt)"}
 
     # ---- the reference's own measurement conventions, per bit width (both arms print these) -------------------------
     # profile_convention_tops: QGTC.bitMM2Bit_profile (QGTC_device.cu:379-434): 200 repetitions of ONE GEMM on the same
@@ -443,8 +443,8 @@ def run_ours(args):
                          "note": "integer ops/s (2*M*K*N) of gemm_tc05_kernel alone (CUDA events around each of its launches, mean over the four bit "
                                  "widths; the call also runs prep_b_kernel: see per_bit_ms_per_call), against the INT8 peak the metric names = 2 x %s "
                                  "dense bf16 (burst, kernel timed alone; nominal 4500).  by_operand_path quotes each path against the peak of the "
-                                 "instruction it issues (FP4 = 4 x bf16); ncu says the pace is set by the CUDA-core bit expansion and the TMEM ring, "
-                                 "not by the tensor pipe (limiter fields)" % peaks["source"]},
+                                 "instruction it issues (FP4 = 4 x bf16); the limiter fields say what paces each path (MMA dispatch rate on the 4-bit "
+                                 "path, the three-stage TMEM ring on the u8 path)" % peaks["source"]},
             "cpu_baseline": cpu,
             "epochs": epoch,
             "zero_tile_sweep": zero_tiles,

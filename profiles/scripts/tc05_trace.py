@@ -19,7 +19,9 @@ from engine_sweep import run  # noqa: E402
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 0
-    ms, tops = run(capi.ENGINE_TCGEN05, 4096, 4096, N, 2, 128, reps=1, flags=flags)
+    M = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+    bits = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    ms, tops = run(capi.ENGINE_TCGEN05, M, M, N, bits, 128 if M >= 4096 else 1024, reps=1, flags=flags)
     print("ms", ms, "tops", tops)
     buf = np.zeros(8 * 512 * 8, dtype=np.uint64)
     L = capi.lib()

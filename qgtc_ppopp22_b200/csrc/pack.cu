@@ -247,31 +247,40 @@ __global__ void __launch_bounds__(256) count_nonzero_tiles_kernel(Words x1, int 
 // ------------------------------------------------------------------------------------------
 // Tile bitmap for zero-tile jumping in the tcgen05 engine: bit c of word w of tile (z, mt) is set iff the
 // 128-row x 128-bit block (rows 128mt.., K chunk 32w + c) of plane 0 of problem z has any bit set.
-// One warp per (z, mt, w): lane = chunk, 128 coalesced row reads, one ballot.
+// One warp per (z, mt, w, row group of 8): lane = chunk, 8 coalesced row reads (independent loads), one ballot, one atomicOr
+// into the (pre-zeroed) bitmap word.  (The first version walked all 128 rows of a tile in one warp: 57 us for a 759-node batch,
+// pure load latency.)
 // ------------------------------------------------------------------------------------------
+constexpr int kBmRows = 8;       // rows per warp
 __global__ void __launch_bounds__(256) tile_bitmap_kernel(const uint32_t* __restrict__ x1, unsigned long long x1_words,
                                                            unsigned long long bstride, int M, int K, int count,
                                                            uint32_t* __restrict__ bitmap) {
     const int lane = threadIdx.x & 31;
     const int gdk = s128(K), mtiles = (p8(M) + 127) / 128, bmw = (gdk + 31) / 32;
-    const long long units = (long long)count * mtiles * bmw;
+    constexpr int kGroups = 128 / kBmRows;
+    const long long units = (long long)count * mtiles * bmw * kGroups;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long gdk4 = (unsigned long long)gdk * 4;
-    for (long long u = warp_id; u < units; u += nwarps) {
+    for (long long uu = warp_id; uu < units; uu += nwarps) {
+        const int rg = (int)(uu % kGroups);
+        const long long u = uu / kGroups;                 // bitmap word index: (z, mt, w)
         const int w = (int)(u % bmw), mt = (int)((u / bmw) % mtiles), z = (int)(u / ((long long)bmw * mtiles));
         const Words a{x1 + (unsigned long long)z * bstride, x1_words};
         const int c = 32 * w + lane;
         uint32_t any = 0;
         if (c < gdk) {
-            const int r_end = min(128, p8(M) - mt * 128);
-            for (int r = 0; r < r_end; ++r) {
-                const uint4 v = ldw4(a, (unsigned long long)(mt * 128 + r) * gdk4 + 4ull * c);
-                any |= v.x | v.y | v.z | v.w;
+            const int r0 = mt * 128 + rg * kBmRows;
+#pragma unroll
+            for (int r = 0; r < kBmRows; ++r) {
+                if (r0 + r < p8(M)) {
+                    const uint4 v = ldw4(a, (unsigned long long)(r0 + r) * gdk4 + 4ull * c);
+                    any |= v.x | v.y | v.z | v.w;
+                }
             }
         }
         const uint32_t word = __ballot_sync(0xffffffffu, any != 0u);
-        if (lane == 0) bitmap[u] = word;
+        if (lane == 0 && word) atomicOr(bitmap + u, word);
     }
 }
 
@@ -392,7 +401,10 @@ int launch_edges_to_bits(const int* rows, const int* cols, long long n_edges, in
 }
 
 int launch_tile_bitmap(const uint32_t* x1, size_t x1_words, size_t bstride, int M, int K, int count, uint32_t* bitmap, cudaStream_t st) {
-    const long long units = (long long)count * ((p8(M) + 127) / 128) * ((s128(K) + 31) / 32);
+    const long long words = (long long)count * ((p8(M) + 127) / 128) * ((s128(K) + 31) / 32);
+    cudaError_t e = cudaMemsetAsync(bitmap, 0, (size_t)words * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return record_cuda_error(e, "cudaMemsetAsync(tile bitmap)");
+    const long long units = words * (128 / kBmRows);
     const int grid = grid_for((units + 7) / 8, 8);
     tile_bitmap_kernel<<<grid, 256, 0, st>>>(x1, (unsigned long long)x1_words, (unsigned long long)bstride, M, K, count, bitmap);
     note_launch();
