@@ -67,6 +67,9 @@ constexpr int kTmemCols = 512;
 #ifndef QGTC_TC05_SPLIT
 #define QGTC_TC05_SPLIT 0
 #endif
+#ifndef QGTC_TC05_EPI_POLL1
+#define QGTC_TC05_EPI_POLL1 1
+#endif
 #ifndef QGTC_TC05_DENSE_ISSUE
 #define QGTC_TC05_DENSE_ISSUE 1
 #endif
@@ -899,7 +902,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
             const UnitGeo ug = unit_geo<PAIR>(T, group_id + tl * ngroups, rank);
             const int z = ug.z, m = ug.mt * 128 + 32 * q + lane;   // pair mode: rows past the matrix are masked by m < P8(M)
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 0);
-            {   // long wait (a whole tile): sleep between polls instead of the hinted try_wait, which wakes at every barrier event of the CTA
+            // Long wait (a whole tile).  ONE epilogue warp polls the barrier; the others park on a named barrier, which costs them a
+            // single instruction: a polling warp comes back every ~40 ns whatever sleep it asks for (ncu: the instruction count does
+            // not depend on it), and eight of them were a fifth of all instructions this kernel executed -- in a kernel paced by
+            // the SM's instruction throughput.
+            if (!QGTC_TC05_EPI_POLL1 || warp == kEpilogueWarp0) {
                 uint32_t spins = 0;
                 while (!mbar_try_wait(&d_full[buf], duse & 1)) {
                     __nanosleep(T.epi_sleep);
@@ -909,6 +916,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
                     }
                 }
             }
+            if (QGTC_TC05_EPI_POLL1) asm volatile("bar.sync 2, %0;\n" ::"n"(kEpilogueWarps * 32) : "memory");
             tc_fence_after();
             if (warp == kEpilogueWarp0 && lane == 0) QGTC_TRACE(2, tl, 1);
             const uint32_t d_tmem = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * NP);
