@@ -23,7 +23,8 @@ def ops(M, K, N, b, density=0.2):
 
 
 # single problems: ragged tiles, short K, N up to 256, every operand path (fp4: b <= 2, u8 mode 2: b <= 5, mode 1: b = 8)
-for (M, K, N, b) in [(130, 513, 16, 1), (300, 1000, 40, 2), (257, 640, 72, 4), (264, 1100, 200, 8), (8, 128, 8, 2)]:
+# (257 x 640 x 64 at 4 bits and 264 x 1100 x 48 at 8 bits run the compile-time four-chunk instances of the u8 path, 300 x 1000 x 40 at 2 bits the seven-chunk 4-bit instance)
+for (M, K, N, b) in [(130, 513, 16, 1), (300, 1000, 40, 2), (257, 640, 72, 4), (264, 1100, 200, 8), (8, 128, 8, 2), (257, 640, 64, 4), (264, 1100, 48, 8)]:
     A, X, a, x = ops(M, K, N, b)
     want = (A.double() @ X.double()).float()
     got = capi.bitMM2Int(a, x, M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05)
@@ -38,7 +39,7 @@ for (M, K, N, b) in [(130, 513, 16, 1), (300, 1000, 40, 2), (257, 640, 72, 4), (
         bad.append(("tilemap", M, K, N, b))
 
 # many short ragged problems in one launch (the case that exposed the issuer phase race in round 1)
-for (M, K, N, b, cnt) in [(130, 513, 64, 2, 40), (264, 1100, 16, 1, 40), (129, 385, 128, 4, 30)]:
+for (M, K, N, b, cnt) in [(130, 513, 64, 2, 40), (264, 1100, 16, 1, 40), (129, 385, 128, 4, 30), (200, 1024, 64, 4, 40), (136, 1920, 32, 8, 24)]:
     A, X, a, x = ops(M, K, N, b, 0.3)
     ref = capi.bitMM2Bit(a, x, M, K, N, 1, b, b, engine=capi.ENGINE_MMA_SYNC)
     out = capi.bitMM2Bit_batched(a, x, cnt, M, K, N, 1, b, b, engine=capi.ENGINE_TCGEN05)
