@@ -101,11 +101,41 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+NUMA_NODE = None     # NUMA node this rank was bound to (the one its GPU hangs off), for the e2e record
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process (and so the pinned host buffers it allocates: first touch) to the CPUs of the NUMA node its GPU is attached to.
+    With one rank per GPU the end-to-end leg is bound by host memory and the PCIe roots; buffers on the far socket halve it."""
+    global NUMA_NODE
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return
+        cpus = set()
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            NUMA_NODE = node
+    except Exception:
+        pass
+
+
 def dist_setup(n):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("QGTC_BENCH_NUMA", "1") != "0":
+        bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -435,7 +465,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_val, 3), "unit": "TOPS (2*M*K*N per GEMM)", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "qgtc_bitmm2bit_host_batched_multi (pinned host operands -> packed results on host; adjacency uploaded once per graph "
                            "for the four bit widths; upload/GEMM/download pipelined)",
-                    "graphs_per_step": Ge * len(BITS), "steps": e2e_steps, "matches_device_result": e2e_ok,
+                    "graphs_per_step": Ge * len(BITS), "steps": e2e_steps, "matches_device_result": e2e_ok, "numa_node_rank0": NUMA_NODE,
                     "rank_s_per_step": stats(e2e_rank_s) if world > 1 else None},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
