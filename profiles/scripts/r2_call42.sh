@@ -1,0 +1,12 @@
+#!/bin/bash
+O=gpurun_out
+timeout 900 python -m pytest tests/test_grp_gpu.py tests/test_drivers_gpu.py tests/test_reference_gpu.py -m gpu -q -x 2>&1 | tail -3 > $O/r2c42_tests.txt
+cat $O/r2c42_tests.txt
+QGTC_GRP_TRACE=1 timeout 200 python profiles/scripts/grp_trace.py agg 2258 75 2 16 > $O/r2c42_grp_trace_arxiv.txt 2>&1
+grep "iss item full\|conv loads landed\|conv full arrive" $O/r2c42_grp_trace_arxiv.txt | head -24
+timeout 600 python bench.py --steps 3 --warmup 3 --no-zero-tile --no-cpu-baseline > $O/r2c42_bench.json 2> $O/r2c42_bench.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2c42_bench.json").read().strip().splitlines()[-1])
+e=d["epochs"]; print("ppi", e["cluster_gcn_ppi_2bit"]["grouped_graph"]["epoch_ms"], "gin", e["batched_gin_2bit"]["epoch_ms"], "arxiv", [e["cluster_gcn_arxiv"][b]["epoch_ms"] for b in ["1_bit","2_bit","4_bit","8_bit"]])
+PY

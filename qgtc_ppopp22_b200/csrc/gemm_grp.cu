@@ -93,6 +93,10 @@ struct GrpArgs {
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// whole piece known to exist: no source-size operand, shared-window destination address formed by the caller
+__device__ __forceinline__ void cp_async16_a(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -413,19 +417,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             uint32_t use = (uint32_t)(g / S);
             // software pipeline: iteration k issues the loads of own item k and consumes own item k - (kARing - 1)
             int it_l = g, slot_l = 0, slot_c = 0;
+            int lu_unit = -1;                      // unit whose row pointer / bounds are cached below
+            unsigned long long lu_act = 0, lu_row0 = 0;
+            const uint32_t* lu_rowp = nullptr;
+            bool lu_row_ok = false, lu_fast = false;
 #pragma unroll 1
             for (int it_c = g - (kARing - 1) * G; it_c < n_items; it_c += G, it_l += G) {
                 if (it_l < n_items) {
                     const ItemRec I = items[it_l];
                     const UnitRec& U = units[I.unit];
-                    const int m = U.mt * 128 + 32 * q + lane;
-                    const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
-                    const unsigned long long act_offset = (unsigned long long)p8(U.M) * gdk4;          // reference kernel.h:265
-                    const unsigned long long idx0 = (unsigned long long)m * gdk4 + 4ull * I.c0;
-                    const bool row_ok = m < p8(U.M);
-                    unsigned char* dst = ring + slot_l * T.a_slot_bytes;
                     const int nb1 = A1 ? 1 : T.bit1;
-                    if (row_ok && idx0 + (unsigned long long)(nb1 - 1) * act_offset + 4ull * I.nch <= U.x1_words) {   // all pieces inside the tensor
+                    if ((int)I.unit != lu_unit) {
+                        // per-unit part of the address arithmetic (64-bit products, bounds): once per unit, not per item -- this
+                        // instruction stream sits between two of the warp's items, i.e. on the group's critical path
+                        lu_unit = I.unit;
+                        const int m = U.mt * 128 + 32 * q + lane;
+                        const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
+                        lu_act = (unsigned long long)p8(U.M) * gdk4;                                     // reference kernel.h:265
+                        lu_row0 = (unsigned long long)m * gdk4;
+                        lu_row_ok = m < p8(U.M);
+                        // every piece of this row, in every plane, lies inside the tensor: plain 16-byte copies from a row pointer
+                        lu_fast = lu_row_ok && lu_row0 + (unsigned long long)(nb1 - 1) * lu_act + gdk4 <= U.x1_words;
+                        lu_rowp = U.x1 + lu_row0;
+                    }
+                    const unsigned long long act_offset = lu_act;
+                    const unsigned long long idx0 = lu_row0 + 4ull * I.c0;
+                    const bool row_ok = lu_row_ok;
+                    unsigned char* dst = ring + slot_l * T.a_slot_bytes;
+                    if (lu_fast) {
+                        const uint32_t d0 = smem_u32(dst);
+                        const uint32_t* src0 = lu_rowp + 4 * I.c0;
+                        for (int p = 0; p < nb1; ++p, src0 += act_offset) {
+#pragma unroll
+                            for (int j = 0; j < kMaxCpsG; ++j)
+                                if (j < I.nch) cp_async16_a(d0 + (uint32_t)((p * CPS + j) * 512), src0 + 4 * j);
+                        }
+                    } else if (row_ok && idx0 + (unsigned long long)(nb1 - 1) * act_offset + 4ull * I.nch <= U.x1_words) {   // all pieces inside the tensor
                         for (int p = 0; p < nb1; ++p)
                             for (int j = 0; j < I.nch; ++j)
                                 cp_async16_zfill(dst + (p * CPS + j) * 512, U.x1 + idx0 + (unsigned long long)p * act_offset + 4 * j, 16);
@@ -559,6 +586,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const int RB = T.b_ring;                                       // staged items in flight (2..4, by shared-memory budget)
         int s = 0, slot_l = 0, slot_c = 0;
         uint32_t use = 0;
+        int lu_unit = -1;                          // unit whose column pointers / bounds are cached below
+        unsigned long long lu_woff = 0;
+        const uint32_t* lu_colp[kMaxTasks] = {nullptr, nullptr};
+        bool lu_fast[kMaxTasks] = {false, false};
 #pragma unroll 1
         for (int it_c = -(RB - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
             if (it_l < n_items) {
@@ -566,11 +597,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 if (!reuse_flag[it_l]) {     // not a stage re-use: stage this item's packed words
                     const UnitRec& U = units[I.unit];
                     const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
-                    const unsigned long long w_offset = gdk4 * (unsigned long long)pn;
+                    if ((int)I.unit != lu_unit) {
+                        // per-unit part of the address arithmetic, once per unit (this stream is the converters' whole critical path
+                        // between two items: ~35 instructions of 64-bit index and bounds arithmetic per copy before, clock64 trace)
+                        lu_unit = I.unit;
+                        lu_woff = gdk4 * (unsigned long long)pn;
+#pragma unroll
+                        for (int i = 0; i < kMaxTasks; ++i) {
+                            const unsigned long long col0 = (unsigned long long)tn_[i] * gdk4;
+                            lu_colp[i] = U.x2 + col0;
+                            // every piece of this column, in every plane, lies inside the tensor
+                            lu_fast[i] = tn_[i] < p8n && col0 + (unsigned long long)(T.bit2 - 1) * lu_woff + gdk4 <= U.x2_words;
+                        }
+                    }
+                    const unsigned long long w_offset = lu_woff;
                     unsigned char* dst = ring + slot_l * T.b_slot_bytes;
 #pragma unroll
                     for (int i = 0; i < kMaxTasks; ++i) {
-                        if (tj[i] < I.nch) {
+                        if (tj[i] < I.nch && lu_fast[i]) {
+                            const uint32_t* src0 = lu_colp[i] + 4 * (I.c0 + tj[i]);
+                            uint32_t d0 = smem_u32(dst) + (uint32_t)(i * T.bit2) * (uint32_t)(kConvThreads * 16);
+                            for (int qq = 0; qq < T.bit2; ++qq, src0 += w_offset, d0 += (uint32_t)(kConvThreads * 16)) cp_async16_a(d0, src0);
+                        } else if (tj[i] < I.nch) {
                             const unsigned long long idx0 = (unsigned long long)tn_[i] * gdk4 + 4ull * (I.c0 + tj[i]);
                             const bool col_ok = tn_[i] < p8n;
                             for (int qq = 0; qq < T.bit2; ++qq) {
