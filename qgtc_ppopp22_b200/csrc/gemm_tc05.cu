@@ -213,8 +213,11 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
     // a column's K run (coalesced 512-byte runs).  Phase 2: thread = (chunk, k group, column), column fastest: the
     // eight columns of one (chunk, k group) store one contiguous 128-byte row of core matrices.
     extern __shared__ uint4 pk4[];   // [bit2][8][ld / 4]
-    // the GEMM grid (launched with programmatic stream serialization) may be scheduled as this grid's blocks retire;
-    // its feature-image loader still waits for this whole grid (griddepcontrol.wait) before the first copy
+    // This grid is itself launched with programmatic stream serialization: it may become resident while the previous kernel of the
+    // stream still runs (which hides its launch latency), so it first waits for that kernel to complete -- x2 may be its output and
+    // the image buffer may still be read by it -- and only then lets the GEMM grid start (whose adjacency pipeline runs beside
+    // this grid; its feature-image loader waits for this whole grid before the first copy).
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     constexpr int bit2 = BIT2;
     const int gdk = P.gdk, n_lim = p8(P.N);
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(256) prep_b_kernel(GemmArgs P, uint8_t* __rest
 template <int BIT2>
 __global__ void __launch_bounds__(256) prep_b4_kernel(GemmArgs P, uint8_t* __restrict__ img, unsigned long long gstride, int NP) {
     extern __shared__ uint4 pk4[];   // [bit2][8][ld4]
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");              // see prep_b_kernel
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int gdk = P.gdk, n_lim = p8(P.N);
     const unsigned long long gdk4 = (unsigned long long)gdk * 4;
@@ -325,6 +329,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
     // the swizzled TMA destinations need 1024-byte alignment: align by hand, the launch adds the slack
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const GemmArgs& P = T.g;
+    // the next kernel of the stream (the next call's prep grid, launched programmatically) may become resident as SMs free up; it
+    // waits for this whole grid before it touches memory
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = T.NP, S = T.stages, gdk = P.gdk, CPS = CPST > 0 ? CPST : T.cps;
     constexpr bool F4 = AMODE == 3;     // 4-bit operand path (only as a compile-time instance)
@@ -1180,14 +1187,26 @@ int launch_gemm_tc05(const GemmArgs& a, int epi, cudaStream_t st) {
         const size_t psmem = (size_t)a.bit2 * 8 * (kPrepChunks + 1) * sizeof(uint4);    // <= 33 KB
         const unsigned long long gs = (unsigned long long)a.gdk * chunk_img_bytes;
         const int halves = pair ? 2 : 1;
+        cudaLaunchConfig_t pcfg = {};
+        pcfg.gridDim = dim3((unsigned)pgrid);
+        pcfg.blockDim = dim3(256);
+        pcfg.dynamicSmemBytes = psmem;
+        pcfg.stream = st;
+        cudaLaunchAttribute pattr[1];
+        pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pattr[0].val.programmaticStreamSerializationAllowed = 1;
+        pcfg.attrs = pattr;
+        static const bool prep_pdl = [] { const char* e = getenv("QGTC_TC05_PREP_PDL"); return !(e && e[0] == '0'); }();
+        pcfg.numAttrs = prep_pdl ? 1 : 0;
+        const int np_ = T.NP;
         if (f4) {
-            if (a.bit2 == 1) prep_b4_kernel<1><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP);
-            else prep_b4_kernel<2><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP);
+            if (a.bit2 == 1) cudaLaunchKernelEx(&pcfg, prep_b4_kernel<1>, pa, img, gs, np_);
+            else cudaLaunchKernelEx(&pcfg, prep_b4_kernel<2>, pa, img, gs, np_);
         } else
 #define QGTC_PREP(B)                                                                              \
     case B:                                                                                       \
-        if (T.amode == 2) prep_b_kernel<B, true><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP, halves); \
-        else prep_b_kernel<B, false><<<(int)pgrid, 256, psmem, st>>>(pa, img, gs, T.NP, halves);  \
+        if (T.amode == 2) cudaLaunchKernelEx(&pcfg, prep_b_kernel<B, true>, pa, img, gs, np_, halves); \
+        else cudaLaunchKernelEx(&pcfg, prep_b_kernel<B, false>, pa, img, gs, np_, halves);          \
         break;
         switch (a.bit2) {
             QGTC_PREP(1) QGTC_PREP(2) QGTC_PREP(3) QGTC_PREP(4) QGTC_PREP(5) QGTC_PREP(6) QGTC_PREP(7) QGTC_PREP(8)
