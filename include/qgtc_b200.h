@@ -83,6 +83,19 @@ void qgtc_packed_shape(int layout, int bits, int H, int W, int64_t* rows, int64_
 int qgtc_val2bit(const float* in_dev, int H, int W, int nbits, int col_major, int output_layer,
                  int32_t* out_dev, size_t out_words, void* stream);
 
+/* val2bit of a whole list of matrices (same nbits and layout) in one call.  The ROW layout (col_major == 0: the batch
+ * adjacencies of sampler.py:97-102, one QGTC.val2bit per batch there) is packed by ONE kernel launch per 448 matrices --
+ * a 759 x 759 adjacency alone is 4 us of launch latency for 2.3 MB; the column-major layouts run one launch per matrix.
+ * Every matrix gets exactly the words qgtc_val2bit would write. */
+typedef struct qgtc_pack_problem {
+    const float* in_dev;   /* fp32 [H, W], row-major, contiguous */
+    int32_t* out_dev;      /* packed result, 16-byte aligned */
+    size_t out_words;      /* capacity of out_dev in 32-bit words (>= qgtc_packed_words) */
+    int H, W;
+} qgtc_pack_problem;
+int qgtc_val2bit_batched(const qgtc_pack_problem* problems_host, int count, int nbits, int col_major, int output_layer,
+                         void* stream);
+
 /* bit2val: unpack to int32 [H,W].  Replaces bit2val_cuda, QGTC_device.cu:135-206 (silent: the
  * reference's debug printf of the whole tensor is not reproduced). */
 int qgtc_bit2val(const int32_t* in_dev, size_t in_words, int nbits, int H, int W, int col_major,

@@ -26,7 +26,7 @@ SYMBOLS = [
     "qgtc_tile_counts", "qgtc_bitmm2bit_batched", "qgtc_bitmm2bit_host", "qgtc_launch_count",
     "qgtc_tile_bitmap_words", "qgtc_tile_bitmap", "qgtc_bitmm2bit_tilemap", "qgtc_bitmm2int_tilemap",
     "qgtc_bitmm2bit_host_batched", "qgtc_edges2bit", "qgtc_bitmm_grouped", "qgtc_bitmm2bit_host_batched_multi",
-    "qgtc_bitmm_grouped_fused",
+    "qgtc_bitmm_grouped_fused", "qgtc_val2bit_batched",
 ]
 
 
@@ -40,6 +40,11 @@ class FusedUpdate(ctypes.Structure):
     """qgtc_fused_update (include/qgtc_b200.h)."""
     _fields_ = [("w_dev", ctypes.c_void_p), ("w_words", ctypes.c_size_t), ("N2", ctypes.c_int), ("bit_w", ctypes.c_int),
                 ("out_bit2", ctypes.c_int), ("kind2", ctypes.c_int), ("pad128", ctypes.c_int)]
+
+
+class PackProblem(ctypes.Structure):
+    """qgtc_pack_problem (include/qgtc_b200.h)."""
+    _fields_ = [("in_dev", ctypes.c_void_p), ("out_dev", ctypes.c_void_p), ("out_words", ctypes.c_size_t), ("H", ctypes.c_int), ("W", ctypes.c_int)]
 
 
 class GroupProblem(ctypes.Structure):
@@ -78,6 +83,7 @@ def lib() -> ctypes.CDLL:
         L.qgtc_packed_shape.argtypes = [i, i, i, i, c.POINTER(c.c_int64), c.POINTER(c.c_int64)]
         L.qgtc_val2bit.argtypes = [vp, i, i, i, i, i, vp, sz, vp]
         L.qgtc_bit2val.argtypes = [vp, sz, i, i, i, i, i, vp, vp]
+        L.qgtc_val2bit_batched.argtypes = [vp, i, i, i, i, vp]
         L.qgtc_bitmm2bit.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2bit_col.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
         L.qgtc_bitmm2int.argtypes = [vp, sz, vp, sz, i, i, i, i, i, i, vp, sz, i, c.c_uint, vp]
@@ -146,6 +152,25 @@ def val2bit(x: torch.Tensor, nbits: int, col_major: bool, output_layer: bool) ->
         out = torch.empty(packed_shape(layout, nbits, H, W), dtype=torch.int32, device=x.device)
         _check(lib().qgtc_val2bit(x.data_ptr(), H, W, nbits, int(col_major), int(output_layer), out.data_ptr(), out.numel(), _stream()), "val2bit")
     return out
+
+
+def val2bit_batched(xs, nbits: int, col_major: bool, output_layer: bool):
+    """qgtc_val2bit_batched: val2bit of a list of fp32 matrices in one call (ROW layout: one launch for the whole list).
+    Returns the list of packed tensors QGTC.val2bit would return for each of them."""
+    if len(xs) == 0:
+        return []
+    for x in xs:
+        _req_cuda(x, torch.float32, "input")
+    layout = LAYOUT_ROW if not col_major else (LAYOUT_COL8 if output_layer else LAYOUT_COL128)
+    dev = xs[0].device
+    with torch.cuda.device(dev):
+        outs = [torch.empty(packed_shape(layout, nbits, x.shape[0], x.shape[1]), dtype=torch.int32, device=dev) for x in xs]
+        arr = (PackProblem * len(xs))()
+        for i, (x, o) in enumerate(zip(xs, outs)):
+            arr[i].in_dev, arr[i].out_dev, arr[i].out_words = x.data_ptr(), o.data_ptr(), o.numel()
+            arr[i].H, arr[i].W = x.shape[0], x.shape[1]
+        _check(lib().qgtc_val2bit_batched(ctypes.addressof(arr), len(xs), nbits, int(col_major), int(output_layer), _stream()), "val2bit_batched")
+    return outs
 
 
 def bit2val(w: torch.Tensor, nbits: int, H: int, W: int, col_major: bool, output_layer: bool = False) -> torch.Tensor:

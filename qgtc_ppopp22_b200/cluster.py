@@ -201,7 +201,7 @@ class ClusterIter:
             else:
                 A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
                 A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
-                bit_A = ops.val2bit(A, 1, False, False)
+                bit_A = ops.val2bit(A, 1, False, False)                 # (capi.val2bit_batched packs a whole list of them in one launch)
             bit_X = ops.val2bit(X, self.bit_width, True, False)
             if tile_bitmaps:
                 # built once, when the batch is packed (the reference re-tests every 8 x 128 tile inside every GEMM, kernel.h:574-591)

@@ -14,6 +14,7 @@ namespace qgtc {
 
 // kernels (other translation units)
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st);
+int launch_val2bit_row_batched(const float* const* ins, const int* Hs, const int* Ws, uint32_t* const* outs, int count, int nbits, cudaStream_t st);
 int launch_bit2val(const uint32_t* in, size_t in_words, int nbits, int H, int W, int col_major, int* out, cudaStream_t st);
 int launch_count_nonzero_tiles(const uint32_t* x1, size_t x1_words, int M, int K, int bit1, unsigned long long* nz_dev, cudaStream_t st);
 int launch_edges_to_bits(const int* rows, const int* cols, long long n_edges, int H, int W, uint32_t* out, size_t out_words, cudaStream_t st);
@@ -218,6 +219,39 @@ int qgtc_val2bit(const float* in_dev, int H, int W, int nbits, int col_major, in
     if (out_words < need) return QGTC_ERR_SIZE;
     if (int rc = check_device()) return rc;
     return launch_val2bit(in_dev, H, W, nbits, layout, reinterpret_cast<uint32_t*>(out_dev), need, (cudaStream_t)stream);
+}
+
+int qgtc_val2bit_batched(const qgtc_pack_problem* problems_host, int count, int nbits, int col_major, int output_layer,
+                         void* stream) {
+    if (!problems_host || count <= 0) return QGTC_ERR_INVALID_ARG;
+    if (!bits_ok(nbits)) return QGTC_ERR_UNSUPPORTED;
+    const int layout = !col_major ? QGTC_LAYOUT_ROW : (output_layer ? QGTC_LAYOUT_COL8 : QGTC_LAYOUT_COL128);
+    for (int i = 0; i < count; ++i) {
+        const qgtc_pack_problem& p = problems_host[i];
+        if (!p.in_dev || !p.out_dev || p.H <= 0 || p.W <= 0) return QGTC_ERR_INVALID_ARG;
+        if (!aligned16(p.out_dev)) return QGTC_ERR_ALIGNMENT;
+        if (p.out_words < qgtc_packed_words(layout, nbits, p.H, p.W)) return QGTC_ERR_SIZE;
+    }
+    if (int rc = check_device()) return rc;
+    if (layout != QGTC_LAYOUT_ROW) {       // transposing packs: one launch per matrix
+        for (int i = 0; i < count; ++i) {
+            const qgtc_pack_problem& p = problems_host[i];
+            if (int rc = launch_val2bit(p.in_dev, p.H, p.W, nbits, layout, reinterpret_cast<uint32_t*>(p.out_dev),
+                                        qgtc_packed_words(layout, nbits, p.H, p.W), (cudaStream_t)stream))
+                return rc;
+        }
+        return QGTC_OK;
+    }
+    std::vector<const float*> ins(count);
+    std::vector<uint32_t*> outs(count);
+    std::vector<int> Hs(count), Ws(count);
+    for (int i = 0; i < count; ++i) {
+        ins[i] = problems_host[i].in_dev;
+        outs[i] = reinterpret_cast<uint32_t*>(problems_host[i].out_dev);
+        Hs[i] = problems_host[i].H;
+        Ws[i] = problems_host[i].W;
+    }
+    return launch_val2bit_row_batched(ins.data(), Hs.data(), Ws.data(), outs.data(), count, nbits, (cudaStream_t)stream);
 }
 
 int qgtc_bit2val(const int32_t* in_dev, size_t in_words, int nbits, int H, int W, int col_major,

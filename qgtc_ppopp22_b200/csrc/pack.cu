@@ -82,6 +82,203 @@ __global__ void __launch_bounds__(256) pack_row_shfl_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// Batched ROW pack: one launch packs a whole list of matrices (the 75 dense batch adjacencies of a Cluster-GCN epoch are
+// 759 x 759 each: one launch per matrix is 4 us of launch latency for 2.3 MB).  Work unit = (matrix, row, 128-column
+// group), units of all matrices in one index space; the matrix of a unit is found by a binary search over the unit
+// prefix sums in the kernel parameters (once per unit = 512 bytes of input).  Rows of odd width are only 4-byte aligned:
+// a lane then reads the two aligned 16-byte pieces that cover its four columns and picks them apart with the row's
+// misalignment (0..3 floats, warp-uniform per row), so every request is still a full, coalesced 512-byte warp access.
+// ------------------------------------------------------------------------------------------
+constexpr int kPackBatchMax = 448;      // problems per launch (28 bytes each: a 12.5 KB kernel parameter); longer lists are split
+struct PackProblem {
+    const float* in;
+    uint32_t* out;
+    int H, W;
+    unsigned int unit0;                 // first unit of this matrix
+};
+struct PackBatchArgs {
+    int count, nbits;
+    unsigned int units;
+    PackProblem p[kPackBatchMax];
+};
+
+__global__ void __launch_bounds__(256) pack_row_batched_kernel(const __grid_constant__ PackBatchArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int nbits = A.nbits;
+    const float ub = (float)(1 << nbits);
+    const uint32_t keep4 = ((1u << nbits) - 1u) * 0x01010101u;
+    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int p_of_lane = lane & 7, w_of_lane = lane >> 3;
+    int z = 0;
+    for (unsigned u = warp_id; u < A.units; u += nwarps) {
+        if (!(u >= A.p[z].unit0 && (z + 1 == A.count || u < A.p[z + 1].unit0))) {   // usually the same matrix as the last unit
+            int lo = 0, hi = A.count - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (A.p[mid].unit0 <= u) lo = mid; else hi = mid - 1;
+            }
+            z = lo;
+        }
+        const PackProblem& P = A.p[z];
+        const int H = P.H, W = P.W;
+        const int gdy = s128(W);
+        const size_t wpr = (size_t)gdy * 4, plane = (size_t)p8(H) * wpr;
+        const unsigned lu = u - P.unit0;
+        const int r = (int)(lu / (unsigned)gdy), cg = (int)(lu - (unsigned)r * (unsigned)gdy);
+        const int c = cg * 128 + 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < H && c < W) {
+            const float* src = P.in + (size_t)r * W + c;
+            const unsigned mis = (unsigned)((reinterpret_cast<uintptr_t>(src) >> 2) & 3u);   // floats past a 16-byte boundary (warp-uniform)
+            if (mis == 0 && c + 4 <= W) {
+                v = __ldcs(reinterpret_cast<const float4*>(src));
+            } else if (c + 4 <= W && c + 8 <= W + (int)mis) {
+                // two aligned pieces cover the four columns; both stay inside the row's own storage except possibly the very
+                // first / last piece of the whole matrix, which is excluded by the conditions around this branch
+                const float4* a = reinterpret_cast<const float4*>(src - mis);
+                const bool first_ok = (r > 0 || c >= (int)mis);          // piece a[0] starts before the matrix only for row 0, column 0
+                if (first_ok) {
+                    const float4 lo4 = __ldcs(a), hi4 = __ldcs(a + 1);
+                    const float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                    v.x = mis == 1 ? f[1] : (mis == 2 ? f[2] : f[3]);
+                    v.y = mis == 1 ? f[2] : (mis == 2 ? f[3] : f[4]);
+                    v.z = mis == 1 ? f[3] : (mis == 2 ? f[4] : f[5]);
+                    v.w = mis == 1 ? f[4] : (mis == 2 ? f[5] : f[6]);
+                } else {
+                    v.x = __ldcs(src); v.y = __ldcs(src + 1); v.z = __ldcs(src + 2); v.w = __ldcs(src + 3);
+                }
+            } else {
+                v.x = __ldcs(src);
+                if (c + 1 < W) v.y = __ldcs(src + 1);
+                if (c + 2 < W) v.z = __ldcs(src + 2);
+                if (c + 3 < W) v.w = __ldcs(src + 3);
+            }
+        }
+        const uint32_t a0 = quantize_bits(v.x, ub), a1 = quantize_bits(v.y, ub);
+        const uint32_t a2 = quantize_bits(v.z, ub), a3 = quantize_bits(v.w, ub);
+        const uint32_t t = __byte_perm(__byte_perm(a3, a2, 0x0040u), __byte_perm(a1, a0, 0x0040u), 0x5410u) & keep4;
+        unsigned mine = 0;
+        for (int p = 0; p < nbits; ++p) {
+            const unsigned nib = (((t >> p) & 0x01010101u) * 0x01020408u) >> 24;
+            unsigned w = nib << (28 - 4 * p_of_lane);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if (p_of_lane == p) mine = w;
+        }
+        if (p_of_lane < nbits) P.out[(size_t)p_of_lane * plane + (size_t)r * wpr + (size_t)cg * 4 + w_of_lane] = mine;
+    }
+}
+
+// Batched ROW pack, word-per-lane form (rows of at least 16 output words): a lane owns one output word = 32 consecutive
+// columns = 128 bytes of the fp32 row, as in pack_row_kernel below; a unit is (matrix, row, group of 32 words).  Rows of odd
+// width are only 4-byte aligned: the lane reads the nine aligned 16-byte pieces that cover its 32 floats and the register
+// selection is fixed at compile time per misalignment (0..3 floats, the same for every lane of a row).  ~150 instructions per
+// 4 KB of input instead of ~100 per 512 bytes in the shuffle form above.
+template <int MIS>
+__device__ __forceinline__ void quantize_from_pieces(const float4 (&a)[9], float ub, uint32_t keep4, uint32_t (&t)[8]) {
+    const float f[36] = {a[0].x, a[0].y, a[0].z, a[0].w, a[1].x, a[1].y, a[1].z, a[1].w, a[2].x, a[2].y, a[2].z, a[2].w,
+                         a[3].x, a[3].y, a[3].z, a[3].w, a[4].x, a[4].y, a[4].z, a[4].w, a[5].x, a[5].y, a[5].z, a[5].w,
+                         a[6].x, a[6].y, a[6].z, a[6].w, a[7].x, a[7].y, a[7].z, a[7].w, a[8].x, a[8].y, a[8].z, a[8].w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t a0 = quantize_bits(f[MIS + 4 * k], ub), a1 = quantize_bits(f[MIS + 4 * k + 1], ub);
+        const uint32_t a2 = quantize_bits(f[MIS + 4 * k + 2], ub), a3 = quantize_bits(f[MIS + 4 * k + 3], ub);
+        t[k] = __byte_perm(__byte_perm(a3, a2, 0x0040u), __byte_perm(a1, a0, 0x0040u), 0x5410u) & keep4;
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256) pack_row_batched_word_kernel(const __grid_constant__ PackBatchArgs A) {
+    const int lane = threadIdx.x & 31;
+    const float ub = (float)(1 << NB);
+    const uint32_t keep4 = ((1u << NB) - 1u) * 0x01010101u;
+    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int kU = 1;                 // units per iteration (2: measured slower -- 125 registers halve the occupancy)
+    int z = 0;
+    for (unsigned u0 = warp_id * kU; u0 < A.units; u0 += nwarps * kU) {
+        float4 a[kU][9];
+        const float* src[kU];
+        uint32_t* dst[kU];
+        size_t plane[kU];
+        int col0[kU], W_[kU];
+        unsigned mis[kU];
+        int mode[kU];                     // 0: nothing to do, 1: zeros (padding row / columns), 2: aligned pieces, 3: element-wise tail
+#pragma unroll
+        for (int i = 0; i < kU; ++i) {
+            const unsigned u = u0 + i;
+            mode[i] = 0;
+            if (u >= A.units) continue;
+            if (!(u >= A.p[z].unit0 && (z + 1 == A.count || u < A.p[z + 1].unit0))) {
+                int lo = 0, hi = A.count - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (A.p[mid].unit0 <= u) lo = mid; else hi = mid - 1;
+                }
+                z = lo;
+            }
+            const PackProblem& P = A.p[z];
+            const int H = P.H, W = P.W;
+            const int wpr = s128(W) * 4, groups = (wpr + 31) >> 5;
+            const unsigned lu = u - P.unit0;
+            const int r = (int)(lu / (unsigned)groups), g = (int)(lu - (unsigned)r * (unsigned)groups);
+            const int wi = g * 32 + lane;
+            if (wi >= wpr) continue;
+            plane[i] = (size_t)p8(H) * wpr;
+            dst[i] = P.out + (size_t)r * wpr + wi;
+            col0[i] = wi * 32;
+            W_[i] = W;
+            mode[i] = 1;
+            if (r < H && col0[i] < W) {
+                src[i] = P.in + (size_t)r * W + col0[i];
+                mis[i] = (unsigned)((reinterpret_cast<uintptr_t>(src[i]) >> 2) & 3u);
+                // all nine aligned pieces lie inside the matrix: not before its first element, not past its last
+                const bool whole = col0[i] + 32 <= W && (mis[i] == 0 || ((r > 0 || col0[i] > 0) && (col0[i] + 36 <= W || r + 1 < H)));
+                mode[i] = whole ? 2 : 3;
+                if (whole) {
+                    const float4* ap = reinterpret_cast<const float4*>(src[i] - mis[i]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(a[i][k].x), "=f"(a[i][k].y), "=f"(a[i][k].z), "=f"(a[i][k].w) : "l"(ap + k));
+                    a[i][8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mis[i]) asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(a[i][8].x), "=f"(a[i][8].y), "=f"(a[i][8].z), "=f"(a[i][8].w) : "l"(ap + 8));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kU; ++i) {
+            if (mode[i] == 0) continue;
+            uint32_t t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = 0u;
+            if (mode[i] == 2) {
+                switch (mis[i]) {      // the same for every lane of a row
+                    case 0: quantize_from_pieces<0>(a[i], ub, keep4, t); break;
+                    case 1: quantize_from_pieces<1>(a[i], ub, keep4, t); break;
+                    case 2: quantize_from_pieces<2>(a[i], ub, keep4, t); break;
+                    default: quantize_from_pieces<3>(a[i], ub, keep4, t); break;
+                }
+            } else if (mode[i] == 3) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t q[4] = {0x4B400000u, 0x4B400000u, 0x4B400000u, 0x4B400000u};   // quantize_bits(0)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (col0[i] + 4 * k + e < W_[i]) q[e] = quantize_bits(__ldg(src[i] + 4 * k + e), ub);
+                    t[k] = __byte_perm(__byte_perm(q[3], q[2], 0x0040u), __byte_perm(q[1], q[0], 0x0040u), 0x5410u) & keep4;
+                }
+            }
+            uint32_t w[NB];
+            planes_from_bytes<NB>(t, w);
+#pragma unroll
+            for (int p = 0; p < NB; ++p) dst[i][(size_t)p * plane[i]] = w[p];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // ROW layout: word [p][r][w] holds columns 32w..32w+31 of row r, MSB-first.
 // A lane owns one output word = 32 consecutive columns = one 128-byte line of the fp32 row (eight 16-byte loads, all in
 // flight together); a warp covers 1024 columns of a row per unit and stores 32 consecutive words per plane (one coalesced
@@ -370,6 +567,54 @@ int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_
 #undef QGTC_PACK_COL
     note_launch();
     return check_launch("pack_col_kernel");
+}
+
+// Batched ROW pack of `count` matrices (ins[i]: H[i] x W[i] fp32, outs[i]: its R(nbits, H, W) words) in ceil(count / kPackBatchMax) launches.
+int launch_val2bit_row_batched(const float* const* ins, const int* Hs, const int* Ws, uint32_t* const* outs, int count, int nbits, cudaStream_t st) {
+    static thread_local PackBatchArgs A;
+    for (int base = 0; base < count; base += kPackBatchMax) {
+        const int n = count - base < kPackBatchMax ? count - base : kPackBatchMax;
+        unsigned long long units = 0;
+        for (int i = 0; i < n; ++i) {
+            A.p[i].in = ins[base + i];
+            A.p[i].out = outs[base + i];
+            A.p[i].H = Hs[base + i];
+            A.p[i].W = Ws[base + i];
+            A.p[i].unit0 = (unsigned int)units;
+            units += (unsigned long long)p8(Hs[base + i]) * (unsigned long long)s128(Ws[base + i]);
+            if (units >= (1ull << 31)) return QGTC_ERR_UNSUPPORTED;
+        }
+        A.count = n;
+        A.nbits = nbits;
+        // rows of at least 16 output words everywhere: the word-per-lane form (units = (matrix, row, group of 32 words)); else the shuffle form
+        static const int form_env = [] { const char* e = getenv("QGTC_PACK_BATCHED"); return e ? (e[0] == 'w' ? 1 : (e[0] == 's' ? 2 : 0)) : 0; }();
+        bool wide = true;
+        for (int i = 0; i < n; ++i) wide = wide && s128(A.p[i].W) * 4 >= 16;
+        if (form_env == 1) wide = true;
+        if (form_env == 2) wide = false;
+        if (wide) {
+            units = 0;
+            for (int i = 0; i < n; ++i) {
+                A.p[i].unit0 = (unsigned int)units;
+                units += (unsigned long long)p8(A.p[i].H) * (unsigned long long)((s128(A.p[i].W) * 4 + 31) >> 5);
+            }
+        }
+        A.units = (unsigned int)units;
+        const int grid = grid_for((long long)((units + 7) / 8), 8);
+        if (wide) {
+#define QGTC_PACK_BW(NB) case NB: pack_row_batched_word_kernel<NB><<<grid, 256, 0, st>>>(A); break;
+            switch (nbits) {
+                QGTC_PACK_BW(1) QGTC_PACK_BW(2) QGTC_PACK_BW(3) QGTC_PACK_BW(4) QGTC_PACK_BW(5) QGTC_PACK_BW(6) QGTC_PACK_BW(7) QGTC_PACK_BW(8)
+                default: return QGTC_ERR_UNSUPPORTED;
+            }
+#undef QGTC_PACK_BW
+        } else {
+            pack_row_batched_kernel<<<grid, 256, 0, st>>>(A);
+        }
+        note_launch();
+        if (int rc = check_launch("pack_row_batched_kernel")) return rc;
+    }
+    return QGTC_OK;
 }
 
 int launch_bit2val(const uint32_t* in, size_t in_words, int nbits, int H, int W, int col_major, int* out, cudaStream_t st) {

@@ -61,6 +61,47 @@ def test_val2bit_all_layouts(capi, oracle, H, W, nbits):
         assert np.array_equal(back.cpu().numpy(), oracle.bit2val(want, nbits, H, W, cm, ol))
 
 
+@pytest.mark.parametrize("nbits", [1, 2, 8])
+def test_val2bit_batched_equals_per_matrix(capi, oracle, nbits):
+    """qgtc_val2bit_batched: a list of ragged matrices (odd widths: rows only 4-byte aligned; offset storage; tiny and empty-ish
+    shapes) packed in one call equals QGTC.val2bit of every matrix, in all three layouts, and the oracle for the ROW layout."""
+    rng = np.random.default_rng(91 + nbits)
+    shapes = [(759, 759), (130, 129), (1, 5), (8, 128), (300, 2001), (64, 64), (17, 1023), (515, 33), (2, 3)]
+    xs = [rand_features(rng, sh, nbits) for sh in shapes]
+    xs[0][0, 0] = np.nan
+    # one matrix lives at an odd offset inside a larger buffer (its first row is not 16-byte aligned)
+    big = torch.zeros(3 + 130 * 129, dtype=torch.float32, device="cuda")
+    big[3:] = dev(xs[1]).reshape(-1)
+    xd = [dev(x) for x in xs]
+    xd[1] = big[3:].view(130, 129)
+    for cm, ol in [(False, False), (True, False), (True, True)]:
+        got = capi.val2bit_batched(xd, nbits, cm, ol)
+        assert len(got) == len(xs)
+        for x, xdev, g in zip(xs, xd, got):
+            one = capi.val2bit(xdev, nbits, cm, ol)
+            assert g.shape == one.shape and torch.equal(g, one), (x.shape, cm, ol)
+            if not cm:
+                assert np.array_equal(host_u32(g), oracle.val2bit(x, nbits, cm, ol)), x.shape
+    # a list of wide matrices only (every row >= 16 output words): the word-per-lane form, rows misaligned by 0..3 floats
+    wide_shapes = [(759, 759), (300, 2001), (17, 1023), (515, 513), (64, 512), (9, 4096), (130, 601), (33, 1022)]
+    ws = [rand_features(rng, sh, nbits) for sh in wide_shapes]
+    wd = [dev(x) for x in ws]
+    for off, i in ((1, 6), (2, 3), (3, 0)):      # storage offsets of 1, 2, 3 floats
+        h, w = wide_shapes[i]
+        buf = torch.zeros(off + h * w, dtype=torch.float32, device="cuda")
+        buf[off:] = wd[i].reshape(-1)
+        wd[i] = buf[off:].view(h, w)
+    got = capi.val2bit_batched(wd, nbits, False, False)
+    for x, xdev, g in zip(ws, wd, got):
+        assert torch.equal(g, capi.val2bit(xdev, nbits, False, False)), x.shape
+        assert np.array_equal(host_u32(g), oracle.val2bit(x, nbits, False, False)), x.shape
+    # a list longer than one launch's problem table (448)
+    many = [dev(rand_features(rng, (9 + (i % 5), 40 + (i % 7)), nbits)) for i in range(500)]
+    got = capi.val2bit_batched(many, nbits, False, False)
+    for x, g in zip(many, got):
+        assert torch.equal(g, capi.val2bit(x, nbits, False, False))
+
+
 def test_val2bit_full_size_adjacency(capi, coracle):
     # BASELINE config[1]: 4096 x 4096 1-bit adjacency (64 MiB fp32 -> 2 MiB packed)
     rng = np.random.default_rng(3)
