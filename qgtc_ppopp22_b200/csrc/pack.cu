@@ -505,6 +505,8 @@ static int grid_for(long long work_items_per_block_units, int blocks_per_sm) {
     return (int)g;
 }
 
+int launch_val2bit_row_batched(const float* const* ins, const int* Hs, const int* Ws, uint32_t* const* outs, int count, int nbits, cudaStream_t st);
+
 int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_t* out, size_t out_words, cudaStream_t st) {
     if (layout == QGTC_LAYOUT_ROW) {
         const int rows = p8(H), wpr = s128(W) * 4, gdy = s128(W);
@@ -517,6 +519,8 @@ int launch_val2bit(const float* in, int H, int W, int nbits, int layout, uint32_
         bool use_word = vec && W >= 1024 && word_units >= 2ll * kNumSMs * 8;
         if (force == 1) use_word = vec;
         if (force == 2) use_word = false;
+        // (a single large matrix with unaligned rows stays on the shuffle kernel: routed through the batched word kernel, 2258^2 measured
+        // 0.27 of HBM at 1-2 bits against 0.34-0.36 -- too few warp-level units for one matrix; profiles/r2_pack_bench_call48.txt)
         if (use_word) {
             const int grid = grid_for((word_units + 7) / 8, 8);
             const int vec8 = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) & 31u) == 0) ? 1 : 0;
