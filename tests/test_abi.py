@@ -46,6 +46,24 @@ def test_argument_validation_without_gpu():
     assert L.qgtc_launch_count() == 0
 
 
+def test_val2bit_batched_argument_validation_without_gpu():
+    """qgtc_val2bit_batched refuses malformed problem lists before it touches the device."""
+    import ctypes
+    from qgtc_ppopp22_b200 import capi
+    L = capi.lib()
+    assert L.qgtc_val2bit_batched(None, 1, 1, 0, 0, None) == 1
+    arr = (capi.PackProblem * 2)()
+    assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 0, 1, 0, 0, None) == 1        # empty list
+    assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 1        # null pointers / zero sizes
+    assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 9, 0, 0, None) == 2        # bit width outside [1, 8]
+    for i in range(2):
+        arr[i].in_dev, arr[i].out_dev, arr[i].out_words, arr[i].H, arr[i].W = 0x1000, 0x2000, 4, 8, 128
+    arr[1].out_dev = 0x2004
+    assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 3          # output not 16-byte aligned
+    arr[1].out_dev = 0x2010
+    assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 4               # R(1, 8, 128) needs 32 words
+
+
 def test_extension_surface_matches_reference():
     import torch
     import qgtc_ppopp22_b200
