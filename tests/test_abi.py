@@ -57,10 +57,10 @@ def test_val2bit_batched_argument_validation_without_gpu():
     assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 1        # null pointers / zero sizes
     assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 9, 0, 0, None) == 2        # bit width outside [1, 8]
     for i in range(2):
-        arr[i].in_dev, arr[i].out_dev, arr[i].out_words, arr[i].H, arr[i].W = 0x1000, 0x2000, 4, 8, 128
+        arr[i].in_dev, arr[i].out_dev, arr[i].out_words, arr[i].H, arr[i].W = 0x1000, 0x2000, 32, 8, 128
     arr[1].out_dev = 0x2004
     assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 3          # output not 16-byte aligned
-    arr[1].out_dev = 0x2010
+    arr[1].out_dev, arr[1].out_words = 0x2010, 4
     assert L.qgtc_val2bit_batched(ctypes.addressof(arr), 2, 1, 0, 0, None) == 4               # R(1, 8, 128) needs 32 words
 
 
