@@ -23,7 +23,7 @@ def ri(lo, hi):
 
 
 t0 = time.time()
-n_cfg = n_bad = 0
+n_cfg = n_bad = n_unsup = 0
 while time.time() - t0 < budget:
     kind = ri(0, 9)
     if kind < 4:      # headline-like: compile-time instances, several tiles per CTA
@@ -58,12 +58,13 @@ while time.time() - t0 < budget:
         want = (A.double() @ X.double()).float()
         ok = ok and torch.equal(capi.bitMM2Int(a, x, M, K, N, 1, b, True, engine=capi.ENGINE_TCGEN05), want)
     except capi.QgtcError as e:
-        if "unsupported" not in str(e).lower():
-            ok = False
-            print("error", M, K, N, b, ob, cnt, e)
+        n_unsup += 1
+        if "unsupported" not in str(e).lower() or n_unsup <= 3:
+            ok = ok and "unsupported" in str(e).lower()
+            print("error", M, K, N, b, ob, cnt, e, flush=True)
     n_cfg += 1
     if not ok:
         n_bad += 1
         print("MISMATCH", dict(M=M, K=K, N=N, bits=b, out_bit=ob, count=cnt, density=dens), flush=True)
-print("FUZZ_TC05 configs %d mismatches %d seconds %.0f" % (n_cfg, n_bad, time.time() - t0))
+print("FUZZ_TC05 configs %d (refused as unsupported: %d) mismatches %d seconds %.0f" % (n_cfg, n_unsup, n_bad, time.time() - t0))
 sys.exit(1 if n_bad else 0)
