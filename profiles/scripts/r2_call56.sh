@@ -1,0 +1,13 @@
+#!/bin/bash
+O=gpurun_out
+timeout 900 python -m pytest tests/test_grp_gpu.py tests/test_drivers_gpu.py tests/test_reference_gpu.py -m gpu -q -x 2>&1 | tail -3 > $O/r2c56_tests.txt
+cat $O/r2c56_tests.txt
+timeout 200 python profiles/scripts/fuzz_grp.py 60 5 2>&1 | tail -3
+for wv in 0 1; do
+QGTC_GRP_WIDTH=$wv timeout 600 python bench.py --steps 3 --warmup 3 --no-zero-tile --no-cpu-baseline > $O/r2c56_bench_w$wv.json 2> $O/r2c56_bench_w$wv.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r2c56_bench_w$wv.json").read().strip().splitlines()[-1])
+e=d["epochs"]; print("width instances=$wv ppi", e["cluster_gcn_ppi_2bit"]["grouped_graph"]["epoch_ms"], "gin", e["batched_gin_2bit"]["epoch_ms"], "arxiv", [e["cluster_gcn_arxiv"][b]["epoch_ms"] for b in ["1_bit","2_bit","4_bit","8_bit"]])
+PY
+done

@@ -217,6 +217,14 @@ __device__ __forceinline__ uint32_t assemble_planes_rt(int nb, const unsigned ch
     return any;
 }
 
+// BW > 0: the plane count is the kernel's compile-time bit width (one unrolled variant in the code instead of a switch over five:
+// the role loops of this kernel run out of the instruction cache -- collapsing the switches cut an epoch by 5-10 %)
+template <int BW, bool SCALED>
+__device__ __forceinline__ uint32_t assemble_planes_w(int nb, const unsigned char* src, int stride, uint32_t (&r)[32]) {
+    if (BW > 0 && !(SCALED && BW > 5)) return assemble_planes<(BW > 0 ? BW : 1), SCALED>(src, stride, r);
+    return assemble_planes_rt<SCALED>(nb, src, stride, r);
+}
+
 // Half of a chunk (words 2 h and 2 h + 1 of every plane -> 16 registers = k groups 4 h .. 4 h + 3): when an item has at most 64
 // (chunk, column) tasks, two converter threads share each task so that all four converter warps work on every item.
 template <int NB, bool SCALED>
@@ -260,13 +268,21 @@ __device__ __forceinline__ void assemble_half_rt(int nb, const unsigned char* sr
     }
 }
 
+template <int BW, bool SCALED>
+__device__ __forceinline__ void assemble_half_w(int nb, const unsigned char* src, int stride, int h, uint32_t (&r)[16]) {
+    if (BW > 0 && !(SCALED && BW > 5)) { assemble_half<(BW > 0 ? BW : 1), SCALED>(src, stride, h, r); return; }
+    assemble_half_rt<SCALED>(nb, src, stride, h, r);
+}
+
 // fast path first: a plain try_wait (already-complete phases return at once), then the bounded suspending wait
 __device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity, unsigned int* ef, int where) {
     if (!mbar_try_wait(bar, parity)) mbar_wait(bar, parity, ef, where, true);
 }
 
 // A1: single-plane A operand (the adjacency products): the lean expansion.  TRACE: debug instance with a clock64 timeline of CTA 0.
-template <bool A1, bool TRACE>
+// BW: 1 / 2 / 4 / 8 = the launcher guarantees bit2 == out_bit == BW (and bit1 == BW unless A1, and bit_w == out_bit2 == BW when fused):
+// the conversions and epilogues are compiled for that width only; 0 = any widths (run-time switches).
+template <bool A1, bool TRACE, int BW = 0>
 __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_constant__ GrpArgs T) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                             }
                         }
                     } else {
-                        any = A1 ? assemble_planes<1, false>(src + j * 512, 0, r) : assemble_planes_rt<false>(T.bit1, src + j * 512, CPS * 512, r);
+                        any = A1 ? assemble_planes<1, false>(src + j * 512, 0, r) : assemble_planes_w<BW, false>(T.bit1, src + j * 512, CPS * 512, r);
                     }
                     if (nojump || __any_sync(0xffffffffu, any != 0u)) nzmask |= 1u << j;
                     if (j == 0) {   // the first chunk is expanded before the wait: only the store sits behind it
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             cp_async_wait<0>();
             if (t < T.NP2) {
                 uint32_t o[32];
-                assemble_planes_rt<false>(T.bit_w, st0, kConvThreads * 16, o);
+                assemble_planes_w<BW, false>(T.bit_w, st0, kConvThreads * 16, o);
                 unsigned char* dstc = smem + T.off_b2 + (size_t)(t >> 3) * 128 + (t & 7) * 16;
 #pragma unroll
                 for (int kg = 0; kg < 8; ++kg)
@@ -655,8 +671,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     if (split) {
                         if (i == 0) {
                             uint32_t o[16];
-                            if (A1 && mode2) assemble_half_rt<true>(T.bit2, src, kConvThreads * 16, half, o);
-                            else assemble_half_rt<false>(T.bit2, src, kConvThreads * 16, half, o);
+                            if (A1 && mode2) assemble_half_w<BW, true>(T.bit2, src, kConvThreads * 16, half, o);
+                            else assemble_half_w<BW, false>(T.bit2, src, kConvThreads * 16, half, o);
                             unsigned char* dsth = stage + (size_t)tj[0] * NP * 128 + (size_t)(tn_[0] >> 3) * 128 + (tn_[0] & 7) * 16 + (size_t)(4 * half) * (NP / 8) * 128;
 #pragma unroll
                             for (int kg = 0; kg < 4; ++kg)
@@ -665,8 +681,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                         continue;
                     }
                     uint32_t o[32];
-                    if (A1 && mode2) assemble_planes_rt<true>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
-                    else assemble_planes_rt<false>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
+                    if (A1 && mode2) assemble_planes_w<BW, true>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
+                    else assemble_planes_w<BW, false>(T.bit2, src + i * T.bit2 * (kConvThreads * 16), kConvThreads * 16, o);
                     // image of one K chunk: [k group (8)][column block][8 columns][16 B]; k group kg = registers 4 kg .. 4 kg + 3
                     unsigned char* dstc = stage + (size_t)tj[i] * NP * 128 + (size_t)(tn_[i] >> 3) * 128 + (tn_[i] & 7) * 16;
 #pragma unroll
@@ -866,6 +882,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     const int wpr2 = s128(N2) * 4;
                     const unsigned long long opt2 = (unsigned long long)p8(M) * wpr2;
                     uint32_t* out2_row = out2 + (unsigned long long)m * wpr2;
+                    if (BW > 0) {
+                        epi_bits_tile<BW, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2);
+                    } else
                     switch (ob2) {
                         case 1: epi_bits_tile<1, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
                         case 2: epi_bits_tile<2, false, false, false, 1>(d2_tmem, NP2, 0, N2, ob2, 0, rmask, row_ok, out2_row, opt2); break;
@@ -905,7 +924,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 const uint32_t rmask = m < M ? 0xffffffffu : 0u;
                 uint32_t* out_row = out + (unsigned long long)m * wpr;
 #define QGTC_GRP_EPI(OBV, NNV, FASTV) epi_bits_tile<OBV, NNV, FASTV, false, 1>(d_tmem, NP, 0, N, ob, dshift, rmask, row_ok, out_row, opt_offset)
-                if (mode2) {   // 8 x sums, non-negative: byte-parallel requantize up to 4 output bits
+                if (BW > 0) {
+                    if (mode2) QGTC_GRP_EPI(BW, true, (BW <= 4));
+                    else QGTC_GRP_EPI(BW, false, false);
+                } else if (mode2) {   // 8 x sums, non-negative: byte-parallel requantize up to 4 output bits
                     switch (ob) {
                         case 1: QGTC_GRP_EPI(1, true, true); break;
                         case 2: QGTC_GRP_EPI(2, true, true); break;
@@ -1159,8 +1181,30 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             return check_launch("gemm_grp_kernel");
         };
         int rc;
+        // compile-time width instances (QGTC_GRP_WIDTH=0: the generic instances, for A/B runs)
+        static const bool no_width = [] { const char* e = getenv("QGTC_GRP_WIDTH"); return e && e[0] == '0'; }();
+        int bw = 0;
+        if (!no_width && (bit2 == 1 || bit2 == 2 || bit2 == 4 || bit2 == 8) && (epi != kEpiBitsRow || T.fused || out_bit == bit2) &&
+            (epi != kEpiBitsCol || out_bit == bit2) && (bit1 == 1 || bit1 == bit2) &&
+            (!T.fused || (out_bit == bit2 && T.bit_w == bit2 && (T.epi2 == kEpiFloat || T.out_bit2 == bit2))))
+            bw = bit2;
         if (g_grp_trace) rc = bit1 == 1 ? launch(gemm_grp_kernel<true, true>) : launch(gemm_grp_kernel<false, true>);
-        else rc = bit1 == 1 ? launch(gemm_grp_kernel<true, false>) : launch(gemm_grp_kernel<false, false>);
+        else if (bit1 == 1) {
+            switch (bw) {
+                case 1: rc = launch(gemm_grp_kernel<true, false, 1>); break;
+                case 2: rc = launch(gemm_grp_kernel<true, false, 2>); break;
+                case 4: rc = launch(gemm_grp_kernel<true, false, 4>); break;
+                case 8: rc = launch(gemm_grp_kernel<true, false, 8>); break;
+                default: rc = launch(gemm_grp_kernel<true, false>); break;
+            }
+        } else {
+            switch (bw) {
+                case 2: rc = launch(gemm_grp_kernel<false, false, 2>); break;
+                case 4: rc = launch(gemm_grp_kernel<false, false, 4>); break;
+                case 8: rc = launch(gemm_grp_kernel<false, false, 8>); break;
+                default: rc = launch(gemm_grp_kernel<false, false>); break;
+            }
+        }
         if (rc != QGTC_OK) return rc;
         first += n;
     }
