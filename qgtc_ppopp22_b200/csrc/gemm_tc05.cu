@@ -20,7 +20,9 @@
 // column-64-equivalent MMAs) to amortise the per-stage barrier round trips.
 // Warp roles: warps 0-15 adjacency expanders (warp = TMEM lane quarter of one of four groups; a group
 // expands whole items, the groups take the items round-robin), 16-23 epilogue (lane quarter x column half),
-// 24 feature loader, 25 adjacency TMA loader, 26-27 MMA issuers (items round-robin, in-order commits).
+// 24 feature loader, 25 adjacency TMA loader, 26-27 MMA issuers (items round-robin; an item is signalled on its owner's `full`
+// barrier and only its owner commits to its `empty` barrier -- see the issuer loop; pair mode keeps the in-order protocol).
+// The hot configurations (seven chunks per item on the 4-bit path, four on the u8 path) are compile-time instances (CPST).
 // Zero-tile jumping: an expander warp whose 32 rows x 128 bits are all zero reports it; if the whole
 // 128 x 128-bit tile chunk is zero the MMA issuer skips its 4 MMAs.  With a precomputed tile bitmap
 // (qgtc_tile_bitmap) all-zero stages are skipped by every role.
@@ -700,10 +702,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) gemm_tc05_kernel(const Tc05Arg
         // warp needs ~1300 cycles of (latency-bound) instruction stream per item: wait, flags, 16 MMAs with their
         // descriptors, commit.  The issuers take the items round-robin.  Every MMA accumulates (the epilogue
         // leaves the accumulator zeroed), so the order between the issuers does not matter.
-        // Protocol: EVERY issuer waits for EVERY item's `full` phase and commits to its `empty` barrier (count
-        // T.ni); only the owner issues MMAs in between.  A non-owner's commit tracks the MMAs of its own earlier
-        // items, so "item i is done" implies "all earlier items are done" (the expanders' phase arithmetic needs
-        // that order), and no issuer ever skips a phase of a barrier it waits on (mbarrier waits only see parity).
+        // Protocol, pair mode (and builds without kOwnFull / kOwnerCommit): EVERY issuer waits for EVERY item's `full` phase and
+        // commits to its `empty` barrier (count T.ni); only the owner issues MMAs in between.  A non-owner's commit tracks the
+        // MMAs of its own earlier items, so "item i is done" implies "all earlier items are done", and no issuer ever skips a
+        // phase of a barrier it waits on (mbarrier waits only see parity).  Default (kOwnFull): per-owner `full` barriers and
+        // owner-only commits, see the constants at the top of the kernel -- an issuer only ever touches its own items.
         // Each warp runs with warp-uniform state (addresses and descriptors live in uniform registers);
         // one elected lane issues the tcgen05 instructions.
         if (PAIR && rank != 0) {
