@@ -84,6 +84,31 @@ torch::Tensor val2bit(torch::Tensor input, const int nbits, const bool col_major
     return out;
 }
 
+// extension beyond the reference surface: val2bit of a list of matrices in one call (ROW layout: one kernel launch for the list)
+std::vector<torch::Tensor> val2bit_batched(std::vector<torch::Tensor> inputs, const int nbits, const bool col_major, const bool output_layer) {
+    TORCH_CHECK(!inputs.empty(), "inputs must be non-empty");
+    TORCH_CHECK(nbits >= 1 && nbits <= 8, "nbits must be in [1, 8]");
+    const c10::cuda::CUDAGuard guard(inputs[0].device());
+    const int layout = !col_major ? QGTC_LAYOUT_ROW : (output_layer ? QGTC_LAYOUT_COL8 : QGTC_LAYOUT_COL128);
+    std::vector<qgtc_pack_problem> probs(inputs.size());
+    std::vector<torch::Tensor> outs;
+    outs.reserve(inputs.size());
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        const torch::Tensor& x = inputs[i];
+        CHECK_INPUT(x);
+        TORCH_CHECK(x.dim() == 2 && x.scalar_type() == torch::kFloat32, "inputs must be 2-D float32");
+        TORCH_CHECK(x.device() == inputs[0].device(), "inputs must live on one device");
+        const int H = (int)x.size(0), W = (int)x.size(1);
+        TORCH_CHECK(H > 0 && W > 0, "inputs must be non-empty");
+        int64_t r = 0, c = 0;
+        qgtc_packed_shape(layout, nbits, H, W, &r, &c);
+        outs.push_back(torch::empty({r, c}, x.options().dtype(torch::kInt32)));
+        probs[i] = qgtc_pack_problem{x.data_ptr<float>(), outs.back().data_ptr<int32_t>(), (size_t)outs.back().numel(), H, W};
+    }
+    check_status(qgtc_val2bit_batched(probs.data(), (int)probs.size(), nbits, col_major, output_layer, current_stream()), "val2bit_batched");
+    return outs;
+}
+
 torch::Tensor bit2val(torch::Tensor input, const int nbits, const int height, const int width, const bool col_major,
                       const bool output_layer) {
     CHECK_INPUT(input);
@@ -420,6 +445,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("X1s"), py::arg("X2s"), py::arg("Ms"), py::arg("Ks"), py::arg("N"), py::arg("bit1"), py::arg("bit2"), py::arg("out_bit"), py::arg("W"),
           py::arg("N2"), py::arg("bit_w"), py::arg("out_bit2"), py::arg("float_out") = false, py::arg("pad_128") = false,
           py::arg("tile_maps") = std::vector<torch::Tensor>(), py::arg("static_operands") = 0);
+    m.def("val2bit_batched", &val2bit_batched, "val2bit of a list of float32 matrices in one call (ROW layout: one launch for the whole list)");
     m.def("tile_bitmap", &tile_bitmap, "non-zero 128 x 128-bit tile bitmap of a packed 1-bit adjacency (zero-tile jumping)");
     m.def("edges2bit", &edges2bit, "packed 1-bit adjacency R(1,H,W) from int32 edge endpoints (no dense fp32 intermediate)");
     m.attr("__backend__") = "qgtc_b200";

@@ -95,6 +95,11 @@ def test_val2bit_batched_equals_per_matrix(capi, oracle, nbits):
     for x, xdev, g in zip(ws, wd, got):
         assert torch.equal(g, capi.val2bit(xdev, nbits, False, False)), x.shape
         assert np.array_equal(host_u32(g), oracle.val2bit(x, nbits, False, False)), x.shape
+    # the same entry point through the QGTC extension
+    import qgtc_ppopp22_b200
+    Q = qgtc_ppopp22_b200.load_extension()
+    for g, e in zip(got, Q.val2bit_batched(wd, nbits, False, False)):
+        assert torch.equal(g, e)
     # a list longer than one launch's problem table (448)
     many = [dev(rand_features(rng, (9 + (i % 5), 40 + (i % 7)), nbits)) for i in range(500)]
     got = capi.val2bit_batched(many, nbits, False, False)
