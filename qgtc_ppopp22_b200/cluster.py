@@ -186,6 +186,31 @@ class ClusterIter:
         starts = np.searchsorted(ebk, np.arange(self.max + 1))
         self.batch_edges = {}
 
+        # Dense route (sampler.py:87-102: dense fp32 n x n adjacency -> val2bit): with this repo's ops the dense adjacencies are packed by
+        # ONE launch per chunk of batches (val2bit_batched; chunks bounded to 1 GiB of fp32), with the reference's ops one call per batch.
+        dense_bits = {}
+        if not from_edges and hasattr(ops, "val2bit_batched"):
+            pend, pend_bytes = [], 0
+
+            def flush():
+                nonlocal pend, pend_bytes
+                if pend:
+                    for (c, _), b in zip(pend, ops.val2bit_batched([a for _, a in pend], 1, False, False)):
+                        dense_bits[c] = b
+                pend, pend_bytes = [], 0
+
+            for cid in self.batch_ids:
+                n = int(self.batch_nodes[cid].size)
+                if pend_bytes + 4 * n * n > (1 << 30):
+                    flush()
+                A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
+                r_ = torch.from_numpy(local_id[es[starts[cid]:starts[cid + 1]]]).to(self.device)
+                c_ = torch.from_numpy(local_id[ed[starts[cid]:starts[cid + 1]]]).to(self.device)
+                A[r_, c_] = 1.0                                         # duplicate edges collapse, as to_dense() of 0/1 after clip
+                pend.append((cid, A))
+                pend_bytes += 4 * n * n
+            flush()
+
         for cid in self.batch_ids:
             nodes = self.batch_nodes[cid]
             n = int(nodes.size)
@@ -193,15 +218,17 @@ class ClusterIter:
             cols = torch.from_numpy(local_id[ed[starts[cid]:starts[cid + 1]]])
             self.batch_edges[cid] = (rows, cols)
             X = g.feat[torch.from_numpy(nodes)].to(self.device)
+            A = None
             if from_edges:
                 # extension: pack the adjacency straight from the edge list (no dense fp32 n x n intermediate)
                 from . import capi
                 bit_A = capi.edges2bit(rows.to(self.device, torch.int32), cols.to(self.device, torch.int32), n, n)
-                A = None
+            elif cid in dense_bits:
+                bit_A = dense_bits.pop(cid)
             else:
                 A = torch.zeros((n, n), dtype=torch.float32, device=self.device)
                 A[rows.to(self.device), cols.to(self.device)] = 1.0     # duplicate edges collapse, as to_dense() of 0/1 after clip
-                bit_A = ops.val2bit(A, 1, False, False)                 # (capi.val2bit_batched packs a whole list of them in one launch)
+                bit_A = ops.val2bit(A, 1, False, False)
             bit_X = ops.val2bit(X, self.bit_width, True, False)
             if tile_bitmaps:
                 # built once, when the batch is packed (the reference re-tests every 8 x 128 tile inside every GEMM, kernel.h:574-591)
