@@ -27,6 +27,7 @@
 // tile bitmap (qgtc_tile_bitmap), all-zero pipeline stages are skipped by every role (stage 0 of a unit is always visited:
 // it initialises the accumulator).
 #include <cstdlib>
+#include <cstring>
 
 #include "tc05_common.cuh"
 
@@ -51,8 +52,13 @@ constexpr int kMaxBRing = 4;                  // ... per converter thread: 2..4 
 constexpr int kMaxTasks = 2;                  // (chunk, column) conversion tasks per converter thread and item: cps * NP <= 256
 constexpr int kMaxStagesG = 4;
 constexpr int kMaxCpsG = 4;
-constexpr int kGrpMaxProblems = 224;          // kernel-parameter table (64 B each): one launch takes up to this many problems
+constexpr int kGrpMaxProblems = 224;          // kernel-parameter table (80 B each): one launch takes up to this many problems
 constexpr int kUnitTable = 4096;              // launches of up to this many units carry a unit -> problem table (no search on the device)
+// The tables travel BY VALUE as kernel parameters, and a launch costs ~45 ns per KB of parameters (0.6 us with 64 B, 1.8 us with
+// 28 KB: profiles/r2_launch_floor_call64.txt), so the width instances exist for three table sizes and the launcher picks the
+// smallest that holds the launch: 2.5 KB (a rank's share of an epoch at 4-8 GPUs), 8 KB (75 batches of <= 20 tiles), 22 KB.
+constexpr int kTierSProblems = 24, kTierSUnits = 512;
+constexpr int kTierMProblems = 80, kTierMUnits = 1536;
 constexpr int kMaxUnitsPerCta = 384;          // per-CTA unit records in shared memory (64 B each); larger launches are split by the host
 constexpr int kTraceRoles = 8, kTraceEvents = 256;   // QGTC_GRP_TRACE=1: [role][event][tag, clock64] of CTA 0
 
@@ -71,7 +77,7 @@ struct GrpProblem {
 static_assert(sizeof(GrpProblem) == 80, "problem descriptors are 80 bytes");
 constexpr int kDescWords = (int)(sizeof(GrpProblem) / 4);
 
-struct GrpArgs {
+struct GrpHead {
     int count, units;
     int N, NP, bit1, bit2, out_bit, epi, pad128;
     int cps, stages, dbufs, groups;           // chunks per item, A/B ring depth, accumulator buffers, expander groups in use
@@ -86,9 +92,17 @@ struct GrpArgs {
     int a2_col, d2_col, off_b2;               // TMEM columns of the A2 operand / the second accumulator, smem offset of W's image
     const uint32_t* w2;
     unsigned long long w2_words;
-    GrpProblem p[kGrpMaxProblems];
-    unsigned short unit_z[kUnitTable];        // problem of unit u (valid when units <= kUnitTable)
 };
+template <int NPROB, int NUNIT>
+struct GrpArgsT : GrpHead {
+    static constexpr int kProblems = NPROB, kUnits = NUNIT;
+    GrpProblem p[NPROB];
+    unsigned char unit_z[NUNIT];              // problem of unit u (valid when units <= NUNIT)
+};
+using GrpArgs = GrpArgsT<kGrpMaxProblems, kUnitTable>;
+using GrpArgsM = GrpArgsT<kTierMProblems, kTierMUnits>;
+using GrpArgsS = GrpArgsT<kTierSProblems, kTierSUnits>;
+static_assert(kGrpMaxProblems <= 256, "unit_z holds problem indices in a byte");
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
@@ -282,8 +296,9 @@ __device__ __forceinline__ void gwait(uint64_t* bar, uint32_t parity, unsigned i
 // A1: single-plane A operand (the adjacency products): the lean expansion.  TRACE: debug instance with a clock64 timeline of CTA 0.
 // BW: 1 / 2 / 4 / 8 = the launcher guarantees bit2 == out_bit == BW (and bit1 == BW unless A1, and bit_w == out_bit2 == BW when fused):
 // the conversions and epilogues are compiled for that width only; 0 = any widths (run-time switches).
-template <bool A1, bool TRACE, int BW = 0>
-__global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_constant__ GrpArgs T) {
+// ARGS: the parameter block, i.e. the size of the by-value problem / unit tables (GrpArgs, GrpArgsM, GrpArgsS).
+template <bool A1, bool TRACE, int BW = 0, typename ARGS = GrpArgs>
+__global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_constant__ ARGS T) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     for (int k = warp; k < units_here; k += kThreads / 32) {
         const int u = (int)blockIdx.x + k * (int)gridDim.x;
         int z;
-        if (T.units <= kUnitTable) {
+        if (T.units <= ARGS::kUnits) {
             z = T.unit_z[u];
         } else {
             int lo = 0, hi = T.count - 1;      // largest z with unit0[z] <= u
@@ -1097,7 +1112,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
     unsigned int* ef = tc05_error_flag_device();
     static const bool want_trace = [] { const char* t = getenv("QGTC_GRP_TRACE"); return t && t[0] == '1'; }();
     if (want_trace && !g_grp_trace && cudaMalloc(&g_grp_trace, kGrpTraceWords * 8) != cudaSuccess) { cudaGetLastError(); g_grp_trace = nullptr; }
-    static thread_local GrpArgs T;     // ~23 KB: filled per launch, passed by value as the kernel parameter
+    static thread_local GrpArgs T;     // ~22 KB: filled per launch; passed by value as the kernel parameter, or its used part in a smaller block
     int first = 0;
     int limit = kGrpMaxProblems;       // problems per launch; halved when the per-CTA work lists would not fit shared memory
     while (first < count) {
@@ -1117,7 +1132,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             p.unit0 = (int)units;
             p.mt = 0;
             if (units + u <= kUnitTable)
-                for (long long k = 0; k < u; ++k) T.unit_z[units + k] = (unsigned short)n;
+                for (long long k = 0; k < u; ++k) T.unit_z[units + k] = (unsigned char)n;
             const int nst = (s128(h.K) + pl.cps - 1) / pl.cps;
             if (nst > max_nst) max_nst = nst;
             if (s128(h.K) > max_gdk) max_gdk = s128(h.K);
@@ -1161,7 +1176,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             const double max_sum = (double)max_gdk * 128.0 * (double)((1u << bit2) - 1u);
             T.mode2 = (!no_mode2 && bit1 == 1 && bit2 <= 5 && max_sum * 8.0 < 2147483648.0) ? 1 : 0;
         }
-        auto launch = [&](auto kfn) -> int {
+        auto launch_with = [&](auto kfn, const auto& TA) -> int {
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return record_cuda_error(e, "cudaFuncSetAttribute(gemm_grp)");
             cudaLaunchConfig_t cfg = {};
@@ -1175,10 +1190,17 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             cfg.attrs = attr;
             static const bool no_pdl = [] { const char* e = getenv("QGTC_GRP_NO_PDL"); return e && e[0] == '1'; }();
             cfg.numAttrs = no_pdl ? 0 : 1;
-            e = cudaLaunchKernelEx(&cfg, kfn, T);
+            e = cudaLaunchKernelEx(&cfg, kfn, TA);
             note_launch();
             if (e != cudaSuccess) return record_cuda_error(e, "cudaLaunchKernelEx(gemm_grp)");
             return check_launch("gemm_grp_kernel");
+        };
+        auto launch = [&](auto kfn) -> int { return launch_with(kfn, T); };
+        // the same launch with a smaller parameter block: head + the n problems + the unit table
+        auto shrink = [&](auto& TS) {
+            static_cast<GrpHead&>(TS) = static_cast<const GrpHead&>(T);
+            memcpy(TS.p, T.p, (size_t)n * sizeof(GrpProblem));
+            memcpy(TS.unit_z, T.unit_z, (size_t)T.units);
         };
         int rc;
         // compile-time width instances (QGTC_GRP_WIDTH=0: the generic instances, for A/B runs)
@@ -1188,7 +1210,32 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             (epi != kEpiBitsCol || out_bit == bit2) && (bit1 == 1 || bit1 == bit2) &&
             (!T.fused || (out_bit == bit2 && T.bit_w == bit2 && (T.epi2 == kEpiFloat || T.out_bit2 == bit2))))
             bw = bit2;
-        if (g_grp_trace) rc = bit1 == 1 ? launch(gemm_grp_kernel<true, true>) : launch(gemm_grp_kernel<false, true>);
+        static const bool no_tiers = [] { const char* e = getenv("QGTC_GRP_PARAM_TIERS"); return e && e[0] == '0'; }();
+        const int tier = (no_tiers || g_grp_trace || bw == 0 || (bit1 != 1 && bw == 1)) ? 0
+                         : (n <= kTierSProblems && T.units <= kTierSUnits) ? 2
+                         : (n <= kTierMProblems && T.units <= kTierMUnits) ? 1 : 0;
+#define QGTC_GRP_TIER_CASE(A1_, BW_)                                                         \
+    if (tier == 2) { shrink(TS); rc = launch_with(gemm_grp_kernel<A1_, false, BW_, GrpArgsS>, TS); } \
+    else { shrink(TM); rc = launch_with(gemm_grp_kernel<A1_, false, BW_, GrpArgsM>, TM); }
+        if (tier != 0) {
+            static thread_local GrpArgsS TS;
+            static thread_local GrpArgsM TM;
+            if (bit1 == 1) {
+                switch (bw) {
+                    case 1: QGTC_GRP_TIER_CASE(true, 1) break;
+                    case 2: QGTC_GRP_TIER_CASE(true, 2) break;
+                    case 4: QGTC_GRP_TIER_CASE(true, 4) break;
+                    default: QGTC_GRP_TIER_CASE(true, 8) break;
+                }
+            } else {
+                switch (bw) {
+                    case 2: QGTC_GRP_TIER_CASE(false, 2) break;
+                    case 4: QGTC_GRP_TIER_CASE(false, 4) break;
+                    default: QGTC_GRP_TIER_CASE(false, 8) break;
+                }
+            }
+        } else if (g_grp_trace) rc = bit1 == 1 ? launch(gemm_grp_kernel<true, true>) : launch(gemm_grp_kernel<false, true>);
+#undef QGTC_GRP_TIER_CASE
         else if (bit1 == 1) {
             switch (bw) {
                 case 1: rc = launch(gemm_grp_kernel<true, false, 1>); break;

@@ -164,6 +164,24 @@ def test_grouped_many_problems_and_repeats(capi, coracle):
         assert not bad, bad[:10]
 
 
+@pytest.mark.parametrize("count,M", [(24, 130), (24, 2700), (25, 130), (80, 300), (80, 2500), (81, 130), (224, 40)])
+def test_grouped_parameter_block_sizes(capi, coracle, count, M):
+    """The problem / unit tables travel as kernel parameters in the smallest of three block sizes (24 problems / 512 units,
+    80 / 1536, 224 / 4096): launches on both sides of every boundary, by problem count and by unit count."""
+    N, b, K = 16, 2, 200
+    pool = []
+    for i in range(4):
+        m = M - 3 * i
+        ba, bx, _ = operands(coracle, m, K, N, 1, b, seed=7000 + m)
+        pool.append((m, dev_words(ba), dev_words(bx), dev_words(coracle.bitMM2Bit(ba, bx, m, K, N, 1, b, b))))
+    picks = [pool[i % 4] for i in range(count)]
+    outs = capi.bitmm_grouped([u[1] for u in picks], [u[2] for u in picks], [u[0] for u in picks], [K] * count, N, 1, b, b,
+                              engine=capi.ENGINE_GROUPED)
+    torch.cuda.synchronize()
+    bad = [i for i, (o, u) in enumerate(zip(outs, picks)) if not torch.equal(o, u[3])]
+    assert not bad, bad[:10]
+
+
 @pytest.mark.parametrize("b,K,N", [(2, 50, 16), (4, 128, 121), (1, 300, 64), (8, 16, 16)])
 def test_grouped_shared_weights_stage_reuse(capi, coracle, b, K, N):
     """The weight products of an epoch (X.W, o.W: every problem multiplies with the same packed W, K of one or a few chunks):
