@@ -43,9 +43,9 @@ words = 8 * 256 * 2
 buf = (ctypes.c_ulonglong * words)()
 L.qgtc_debug_grp_trace.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 got = L.qgtc_debug_grp_trace(buf, words)
-NAMES = {1: "kernel start", 2: "after setup sync", 3: "after griddep wait", 4: "kernel end",
-         10: "exp begin", 11: "exp item", 12: "exp loads landed", 13: "exp chunk0 expanded", 14: "exp stage free", 15: "exp full arrive",
-         20: "conv begin", 21: "conv item", 22: "conv loads landed", 23: "conv stage free", 24: "conv full arrive",
+NAMES = {1: "kernel start", 2: "after setup sync", 3: "after griddep wait", 4: "kernel end", 5: "setup: barriers + tmem alloc issued (warp 1)", 6: "setup: unit records done (warp 1)", 7: "setup: first sync passed",
+         10: "exp begin", 11: "exp loads issued", 12: "exp loads landed", 13: "exp chunk0 expanded", 14: "exp stage free", 15: "exp full arrive",
+         20: "conv begin", 21: "conv loads issued", 22: "conv loads landed", 23: "conv stage free", 24: "conv full arrive",
          30: "iss unit", 31: "iss acc free", 32: "iss item full", 33: "iss mmas issued",
          40: "epi unit", 41: "epi acc full", 42: "epi done"}
 ROLES = {0: "expander w0 (g0,q0)", 1: "expander w4 (g1,q0)", 2: "converter w0", 3: "issuer", 4: "epilogue q0", 7: "cta"}

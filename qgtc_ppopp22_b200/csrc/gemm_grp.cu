@@ -83,7 +83,9 @@ struct GrpHead {
     int cps, stages, dbufs, groups;           // chunks per item, A/B ring depth, accumulator buffers, expander groups in use
     int a_slot_bytes, b_slot_bytes, b_stage_bytes, b_ring, max_nst, mode2, any_bitmap;
     int off_bstage, off_bring, off_bars, off_flags, off_misc, off_units;   // shared-memory offsets from the 1024-byte aligned base
-    unsigned int cps_inv;
+    unsigned int cps_inv, np_inv;             // ceil(2^32 / cps), ceil(2^32 / NP): divisions by multiply-high (cps_inv 0: cps == 1)
+    int units_cap;                            // ceil(units / grid): the per-CTA work lists are sized for this many units
+    int may_reuse;                            // some item may find its B stage already converted (shared x2): run the re-use scan
     unsigned flags;
     unsigned int* error_flag;
     unsigned long long* trace;                // clock64 trace buffer (debug instance only), else null
@@ -341,11 +343,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         fence_mbar_init();
     }
     if (warp == kIssuerWarp) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 5);
 
     if (T.any_bitmap && !(T.flags & QGTC_FLAG_X1_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");   // the lists read the tile bitmaps
     // ---- work lists (kernel parameters, and tile bitmaps: nothing here depends on the previous kernel)
-    const int units_here = (T.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int units_cap = (T.units + (int)gridDim.x - 1) / (int)gridDim.x;       // the launcher sized the lists for this many units per CTA
+    // (no run-time divisions in the prologue or the role preambles: this code runs once, cold, on every launch's critical path)
+    const int units_cap = T.units_cap;           // ceil(units / grid): the launcher sized the lists for this many units per CTA
+    const int units_here = units_cap - (((int)blockIdx.x + (units_cap - 1) * (int)gridDim.x >= T.units) ? 1 : 0);
     ItemRec* items = reinterpret_cast<ItemRec*>(smem + T.off_units + units_cap * (int)sizeof(UnitRec));
     unsigned char* reuse_flag = reinterpret_cast<unsigned char*>(items + units_cap * T.max_nst);
     // One warp per unit: the problem index is a warp-uniform constant-bank read, the 64-byte descriptor one read per lane
@@ -375,11 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             r.gdk = s128(P.K);
             r.mt = u - P.unit0;
             r.bm = P.bitmap ? P.bitmap + (size_t)r.mt * ((r.gdk + 31) >> 5) : nullptr;
-            r.item0 = r.bm ? walk_bitmap_stages(r.bm, r.gdk, CPS, T.cps_inv, [](int) {}) : (r.gdk + CPS - 1) / CPS;   // count, for now
+            r.item0 = r.bm ? walk_bitmap_stages(r.bm, r.gdk, CPS, T.cps_inv, [](int) {}) : (T.cps_inv ? (int)__umulhi((unsigned)(r.gdk + CPS - 1), T.cps_inv) : r.gdk);   // count, for now
             units[k] = r;
         }
     }
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 6);
     __syncthreads();
+    if (threadIdx.x == 32) QGTC_GTRACE(7, 7);
     if (warp == 0) {       // item lists: an exclusive scan of the per-unit item counts, then lane k writes the items of unit base + k
         int carry = 0;
         for (int base = 0; base < units_here; base += 32) {
@@ -410,7 +416,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             }
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) *n_items_slot = carry;
+        if (lane == 0) {
+            *n_items_slot = carry;
+            reinterpret_cast<volatile unsigned char*>(n_items_slot)[4] = 0;     // the "never a re-use" flag byte (launches without the re-use scan)
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -444,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             const bool tr = TRACE && trole >= 0 && tlane;
             if (!(T.flags & QGTC_FLAG_X1_STATIC)) asm volatile("griddepcontrol.wait;\n" ::: "memory");
             if (tr) QGTC_GTRACE(trole, 10);
-            int s = g % S;                         // stage and use count of the item being consumed
-            uint32_t use = (uint32_t)(g / S);
+            int s = g;                             // stage and use count of the item being consumed (g < G <= S)
+            uint32_t use = 0;
             // software pipeline: iteration k issues the loads of own item k and consumes own item k - (kARing - 1)
             int it_l = g, slot_l = 0, slot_c = 0;
             int lu_unit = -1;                      // unit whose row pointer / bounds are cached below
@@ -498,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                     if (++slot_l == kARing) slot_l = 0;
                 }
                 cp_async_commit();
+                if (tr) QGTC_GTRACE(trole, 11);
                 if (it_c < 0) continue;
                 cp_async_wait<kARing - 1>();       // this lane's pieces of item it_c have landed (only this lane reads them)
                 if (tr) QGTC_GTRACE(trole, 12);
@@ -564,13 +574,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
             const int task = split ? ((t & 63) + i * 64 * 1024) : (t + i * kConvThreads);   // split: one task per thread (the second is out of range)
-            tj[i] = task / NP;
+            tj[i] = (int)__umulhi((unsigned)task, T.np_inv);
             tn_[i] = task - tj[i] * NP;
         }
         // Stage re-use (one byte per item, written and read by the converters only): an item whose B chunk is identical to those of the S
         // items before it -- the weight products, where every unit multiplies with the same W -- finds its stage already
         // holding the converted image: the converters neither load nor convert anything for it.
-        for (int it = t; it < n_items; it += kConvThreads) {
+        const int n_scan = T.may_reuse ? n_items : 0;   // launcher: no two problems share x2 and no problem spans the grid -> nothing to find
+        for (int it = t; it < n_scan; it += kConvThreads) {
             bool same = it >= S;
             const ItemRec I = items[it];
             const UnitRec& U = units[I.unit];
@@ -611,6 +622,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             if (lane == 0) mbar_arrive(b2_ready);
             asm volatile("bar.sync 1, %0;\n" ::"n"(kConvThreads) : "memory");     // slot 0 is re-used by the main loop's first item
         }
+        // without the scan every item reads the one zero byte next to n_items (index * 0): no flag register lives across the loop
+        const unsigned char* rf = T.may_reuse ? reuse_flag : reinterpret_cast<const unsigned char*>(n_items_slot) + 4;
         unsigned char* ring = b_ring + t * 16;                         // piece (i, plane) of this thread at + (i * bit2 + plane) * 2048
         const bool tr = TRACE && warp == kConvWarp0 && tlane;
         if (tr) QGTC_GTRACE(2, 20);
@@ -625,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         for (int it_c = -(RB - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
             if (it_l < n_items) {
                 const ItemRec I = items[it_l];
-                if (!reuse_flag[it_l]) {     // not a stage re-use: stage this item's packed words
+                if (!rf[it_l * T.may_reuse]) {     // not a stage re-use: stage this item's packed words
                     const UnitRec& U = units[I.unit];
                     const unsigned long long gdk4 = (unsigned long long)U.gdk * 4;
                     if ((int)I.unit != lu_unit) {
@@ -663,9 +676,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
                 }
             }
             cp_async_commit();
+            if (tr) QGTC_GTRACE(2, 21);
             if (it_c < 0) continue;
             const ItemRec I = items[it_c];
-            const bool reuse = reuse_flag[it_c] != 0;
+            const bool reuse = rf[it_c * T.may_reuse] != 0;
             if (!reuse) {
                 if (RB == 4) cp_async_wait<3>();
                 else if (RB == 3) cp_async_wait<2>();
@@ -1161,6 +1175,7 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         T.epi2 = fu ? fu->epi2 : 0; T.pad128_2 = fu ? fu->pad128_2 : 0; T.write_out1 = fu ? fu->write_out1 : 0;
         T.a2_col = pl.a2_col; T.d2_col = pl.d2_col; T.off_b2 = pl.off_b2;
         T.w2 = fu ? fu->w : nullptr; T.w2_words = fu ? fu->w_words : 0;
+        T.np_inv = (unsigned int)((0x100000000ull + (unsigned long long)pl.NP - 1ull) / (unsigned long long)pl.NP);
         T.cps_inv = pl.cps == 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)pl.cps - 1ull) / (unsigned long long)pl.cps);
         T.flags = flags;
         T.error_flag = ef;
@@ -1168,6 +1183,15 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
         if (g_grp_trace) cudaMemsetAsync(g_grp_trace, 0, kGrpTraceWords * 8, st);
         const int grid = T.units < kNumSMs ? T.units : kNumSMs;
         const int units_per_cta = (T.units + grid - 1) / grid;
+        T.units_cap = units_per_cta;
+        {   // stage re-use needs two items of one CTA with the same B chunk: problems sharing x2 (the weight products) or one problem
+            // with more tiles than CTAs.  A cheap sufficient test -- a miss only costs the optimisation, never a result.
+            static const bool force_scan = [] { const char* e = getenv("QGTC_GRP_REUSE_SCAN"); return e && e[0] == '1'; }();
+            int mr = force_scan ? 1 : 0;
+            for (int i = 0; i < n && !mr; ++i)
+                mr = (i > 0 && T.p[i].x2 == T.p[i - 1].x2) || (p8(T.p[i].M) + 127) / 128 > grid;
+            T.may_reuse = mr;
+        }
         const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * ((int)sizeof(ItemRec) + 1);
         T.max_nst = max_nst;
         T.any_bitmap = any_bitmap;
