@@ -85,6 +85,7 @@ struct GrpHead {
     int off_bstage, off_bring, off_bars, off_flags, off_misc, off_units;   // shared-memory offsets from the 1024-byte aligned base
     unsigned int cps_inv, np_inv;             // ceil(2^32 / cps), ceil(2^32 / NP): divisions by multiply-high (cps_inv 0: cps == 1)
     int units_cap;                            // ceil(units / grid): the per-CTA work lists are sized for this many units
+    int conv_alt;                             // <= 64 conversion tasks per item: the two converter half-groups take alternate items (else 0)
     int may_reuse;                            // some item may find its B stage already converted (shared x2): run the re-use scan
     unsigned flags;
     unsigned int* error_flag;
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStagesG; ++s) {
-            mbar_init(&full[s], 4 + kConvWarps);
+            mbar_init(&full[s], 4 + (T.conv_alt ? kConvWarps / 2 : kConvWarps));
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -566,14 +567,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const int t = threadIdx.x - kConvWarp0 * 32;
         const int p8n = p8(T.N);
         const int pn = T.pad128 ? p128(T.N) : p8n;                     // columns per plane of X2: kernel.h:266 / :836
-        // At most 64 tasks per item (cps * NP <= 64, e.g. N = 16): two threads share a task, each converting one half of the chunk
-        // (threads 0-63: words 0-1, threads 64-127: words 2-3), so that all four converter warps work on every item.
-        const bool split = CPS * NP <= 64;
+        // At most 64 tasks per item (cps * NP <= 64, e.g. N = 16): one task per thread and 64 threads per item.  conv_alt (default): the two
+        // half-groups (threads 0-63 / 64-127) take alternate items -- the converters' per-item chain (issue the loads, wait, convert, arrive)
+        // is the engine's critical path, and this runs two of them side by side.  Otherwise two threads share a task, each converting
+        // one half of the chunk (threads 0-63: words 0-1, threads 64-127: words 2-3).
+        const bool few = CPS * NP <= 64;
+        const bool split = few && !T.conv_alt;
         const int half = split ? (t >> 6) : 0;
+        const int cg = T.conv_alt ? (t >> 6) : 0;                      // this thread's item parity; items advance by 1 + conv_alt
         int tj[kMaxTasks], tn_[kMaxTasks];                             // this thread's tasks: chunk within the item, column
 #pragma unroll
         for (int i = 0; i < kMaxTasks; ++i) {
-            const int task = split ? ((t & 63) + i * 64 * 1024) : (t + i * kConvThreads);   // split: one task per thread (the second is out of range)
+            const int task = few ? ((t & 63) + i * 64 * 1024) : (t + i * kConvThreads);   // few: one task per thread (the second is out of range)
             tj[i] = (int)__umulhi((unsigned)task, T.np_inv);
             tn_[i] = task - tj[i] * NP;
         }
@@ -628,14 +633,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
         const bool tr = TRACE && warp == kConvWarp0 && tlane;
         if (tr) QGTC_GTRACE(2, 20);
         const int RB = T.b_ring;                                       // staged items in flight (2..4, by shared-memory budget)
-        int s = 0, slot_l = 0, slot_c = 0;
+        int s = cg, slot_l = 0, slot_c = 0;        // (cg < 2 <= S)
         uint32_t use = 0;
         int lu_unit = -1;                          // unit whose column pointers / bounds are cached below
         unsigned long long lu_woff = 0;
         const uint32_t* lu_colp[kMaxTasks] = {nullptr, nullptr};
         bool lu_fast[kMaxTasks] = {false, false};
 #pragma unroll 1
-        for (int it_c = -(RB - 1), it_l = 0; it_c < n_items; ++it_c, ++it_l) {
+        for (int it_c = cg - (1 + T.conv_alt) * (RB - 1), it_l = cg; it_c < n_items; it_c += 1 + T.conv_alt, it_l += 1 + T.conv_alt) {
             if (it_l < n_items) {
                 const ItemRec I = items[it_l];
                 if (!rf[it_l * T.may_reuse]) {     // not a stage re-use: stage this item's packed words
@@ -723,7 +728,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grp_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (tr) QGTC_GTRACE(2, 24);
-            if (++s == S) { s = 0; ++use; }
+            s += 1 + T.conv_alt;
+            if (s >= S) { s -= S; ++use; }
         }
         cp_async_wait<0>();
     } else if (warp == kIssuerWarp) {
@@ -1191,6 +1197,10 @@ int launch_gemm_grouped(const GroupedProblemHost* probs, int count, int N, int b
             for (int i = 0; i < n && !mr; ++i)
                 mr = (i > 0 && T.p[i].x2 == T.p[i - 1].x2) || (p8(T.p[i].M) + 127) / 128 > grid;
             T.may_reuse = mr;
+        }
+        {
+            static const bool no_alt = [] { const char* e = getenv("QGTC_GRP_CONV_ALT"); return e && e[0] == '0'; }();
+            T.conv_alt = (!no_alt && pl.cps * pl.NP <= 64) ? 1 : 0;
         }
         const int smem_total = pl.smem_total + units_per_cta * (int)sizeof(UnitRec) + units_per_cta * max_nst * ((int)sizeof(ItemRec) + 1);
         T.max_nst = max_nst;
