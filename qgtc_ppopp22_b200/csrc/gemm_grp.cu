@@ -98,7 +98,7 @@ struct GrpHead {
 };
 template <int NPROB, int NUNIT>
 struct GrpArgsT : GrpHead {
-    static constexpr int kProblems = NPROB, kUnits = NUNIT;
+    static constexpr int kUnits = NUNIT;
     GrpProblem p[NPROB];
     unsigned char unit_z[NUNIT];              // problem of unit u (valid when units <= NUNIT)
 };
