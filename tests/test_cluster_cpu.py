@@ -128,3 +128,45 @@ def test_two_rank_sharding_over_gloo():
         assert owned == [1] * len(counts)
         assert tmax == 11.0
         assert gathered_ok
+
+
+class _OracleOps:
+    """The two packing entry points ClusterIter needs, backed by the numpy oracle (CPU tensors)."""
+
+    def __init__(self, oracle, batched):
+        self.o, self.calls, self.batched_calls = oracle, 0, []
+        if batched:
+            self.val2bit_batched = self._batched
+
+    def val2bit(self, x, nbits, col_major, output_layer):
+        self.calls += 1
+        return torch.from_numpy(self.o.val2bit(x.numpy(), nbits, col_major, output_layer).view(np.int32).copy())
+
+    def _batched(self, xs, nbits, col_major, output_layer):
+        self.batched_calls.append(len(xs))
+        return [torch.from_numpy(self.o.val2bit(x.numpy(), nbits, col_major, output_layer).view(np.int32).copy()) for x in xs]
+
+
+def test_cluster_iter_dense_route_batches_the_adjacency_packs(oracle):
+    """Dense route (sampler.py:87-102): ops with val2bit_batched pack all batch adjacencies in one call (in batch order), ops without
+    it (the reference's extension) one call per batch; the packed batches are identical either way and equal the oracle's pack of
+    the induced dense adjacency."""
+    g = C.make_synthetic_graph("tiny", 60)
+    random.seed(2)
+    par = C.shuffled_partitions(g, 60)
+    plain, batched = _OracleOps(oracle, False), _OracleOps(oracle, True)
+    a = C.ClusterIter("tiny", g, 60, 20, None, bit_width=2, device="cpu", ops=plain, par_li=par)
+    b = C.ClusterIter("tiny", g, 60, 20, None, bit_width=2, device="cpu", ops=batched, par_li=par)
+    assert len(a.cTensor_li) == len(b.cTensor_li) == 3
+    assert batched.batched_calls == [3] and batched.calls == 3            # adjacencies: one batched call; features: one call per batch
+    assert plain.calls == 6
+    for i, (ta, tb) in enumerate(zip(a.cTensor_li, b.cTensor_li)):
+        assert torch.equal(ta.bit_A, tb.bit_A) and torch.equal(ta.bit_X, tb.bit_X)
+        nodes = a.batch_nodes[i]
+        n = nodes.size
+        loc = {int(v): k for k, v in enumerate(nodes)}
+        A = np.zeros((n, n), np.float32)
+        for s, d in zip(g.src, g.dst):
+            if int(s) in loc and int(d) in loc:
+                A[loc[int(s)], loc[int(d)]] = 1.0
+        assert np.array_equal(ta.bit_A.numpy().view(np.uint32), oracle.val2bit(A, 1, False, False))
